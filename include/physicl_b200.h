@@ -1,0 +1,188 @@
+/*
+ * physicl_b200.h -- C ABI of the B200 (sm_100a) backend for PhysiCL's per-particle step path.
+ *
+ * The reference (bcwarner/physicl) has no FFI: its device boundary is eight pyopencl calls made
+ * from Python (physicl/__init__.py:428-429, :597, :614, :653, :656, :662).  Each entry point below
+ * names the reference code it stands in for.  All pointers in pcl_soa / params are raw DEVICE
+ * pointers owned by the caller (the Python side keeps torch tensors alive); host-buffer entry
+ * points say so in their name (*_host).  The library allocates only small scratch in pcl_ctx.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; text via pcl_last_error()
+ *   - nothing throws, nothing synchronises unless the name ends in _sync or _host
+ *   - `stream` is a cudaStream_t passed as uintptr_t (0 = legacy default stream)
+ *   - every call does cudaSetDevice(ctx->device) first: the reference calls steps from the
+ *     Simulation thread (physicl/__init__.py:501-516), not the thread that created the context
+ *   - one pcl_ctx per Simulation per GPU; concurrent calls on one ctx are not supported (the
+ *     reference serialises steps under its state lock, physicl/__init__.py:513-516)
+ *
+ * State layout: structure-of-arrays float32 planes in HBM.  A slot whose x is NaN is a retired
+ * (absorbed / escaped) photon; every kernel skips it and every tally excludes it.
+ */
+#ifndef PHYSICL_B200_H
+#define PHYSICL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_ABI_VERSION 1
+#define PCL_MAX_PLANES 8
+
+/* Tally row layout (int64 per column).  Mirrors the rows the reference's measure steps append:
+ * ScatterSignMeasureStep -> [t, N, xp, yp, zp] (physicl/light.py:414-431),
+ * ScatterMeasureStep     -> [t, N, crossings...] (physicl/light.py:374-404). */
+enum {
+    PCL_T_ALIVE = 0,     /* survivors after this step (== len(sim.objects))           */
+    PCL_T_XP = 1,        /* #(v_x > 0) over survivors, strict >  (light.py:424)        */
+    PCL_T_YP = 2,        /* #(v_y > 0)                            (light.py:425)        */
+    PCL_T_ZP = 3,        /* #(v_z > 0)                            (light.py:426)        */
+    PCL_T_SCATTERED = 4, /* photons whose direction was redrawn this step              */
+    PCL_T_ABSORBED = 5,  /* photons removed by delete-mode scattering (light.py:258-260) */
+    PCL_T_ESCAPED = 6,   /* photons retired by the escape sphere this step             */
+    PCL_T_LIVE_IN = 7,   /* live photons entering the step (particle-steps processed)  */
+    PCL_T_PLANE0 = 8,    /* PCL_T_PLANE0 + k : crossings of plane k                    */
+    PCL_TALLY_COLS = 16
+};
+
+typedef struct pcl_ctx pcl_ctx;
+
+/* SoA view of one shard of particles. n = number of slots (live + retired). */
+typedef struct pcl_soa {
+    uint64_t n;
+    float *x, *y, *z;       /* Object.r  (physicl/__init__.py:390)                      */
+    float *vx, *vy, *vz;    /* Object.v  (:393)                                         */
+    float *dx, *dy, *dz;    /* Object.dr (:391), nullable: fused paths keep dr in regs  */
+    float *ax, *ay, *az;    /* Object.a  (:394), nullable                               */
+    float *e;               /* PhotonObject.E / E0 (light.py:34), nullable              */
+    uint32_t *id;           /* local id, nullable => id = slot index                    */
+    uint32_t *nscat;        /* scatter count per photon, nullable (stands in for the    */
+                            /* dv!=0 counting of TracePathMeasureStep, light.py:459-460)*/
+    uint64_t id_base;       /* global id = id_base + local id (RNG counter, sharding)   */
+} pcl_soa;
+
+/* Scatter law of light_scatter_step_sphere / light_scatter_step_del
+ * (physicl/light.py:303-315, :146-158, :239-249). */
+enum {
+    PCL_SCATTER_WAVELENGTH = 1, /* pcoll *= (h c / E)^-4   (light.py:300-301)            */
+    PCL_SCATTER_DELETE = 2      /* scattered photons are removed (light.py:146-158)      */
+};
+typedef struct pcl_scatter_params {
+    float k;       /* A*n, or A*n*(E0/(h c))^4 with PCL_SCATTER_WAVELENGTH (folded in f64 on host) */
+    float c;       /* code-unit speed of light: what str(c) pastes into the kernel (light.py:309) */
+    uint32_t mode; /* PCL_SCATTER_* bits */
+    uint32_t _pad;
+} pcl_scatter_params;
+
+/* Random numbers.  Injected uniforms reproduce the reference, which draws rtheta, rphi, rand per
+ * photon on the host (light.py:285, :235, :181); all three arrays hold U[0,1) float32 values
+ * (the 2*pi / pi scaling of :285 is applied on the device).  When u_rand is NULL the kernel draws
+ * from Philox4x32-10 with key = seed and counter = (global id, step, stream 0). */
+typedef struct pcl_rng {
+    uint64_t seed;
+    uint32_t step;
+    uint32_t _pad;
+    const float *u_theta, *u_phi, *u_rand;
+} pcl_rng;
+
+/* Axis-aligned measurement planes of ScatterMeasureStep (light.py:385-399). */
+typedef struct pcl_planes {
+    uint32_t count;
+    uint32_t axis[PCL_MAX_PLANES]; /* 0,1,2: the one coordinate that is not NaN in `loc` */
+    float loc[PCL_MAX_PLANES];
+} pcl_planes;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* cl.create_some_context() + cl.CommandQueue(ctx)  (physicl/__init__.py:428-429) */
+int pcl_init(int device, pcl_ctx **out);
+int pcl_destroy(pcl_ctx *ctx);
+const char *pcl_last_error(pcl_ctx *ctx); /* ctx may be NULL: last error of this thread */
+int pcl_abi_version(void);
+/* Simulation.get_device_info() (physicl/__init__.py:470-499): name, SM count, bytes of HBM, L2 */
+int pcl_device_info(pcl_ctx *ctx, char *name, int name_len, int *sm_count, uint64_t *hbm_bytes,
+                    uint64_t *l2_bytes);
+/* kernels launched through this ctx so far (bench.py "gpu_launches") */
+uint64_t pcl_launch_count(pcl_ctx *ctx);
+int pcl_stream_sync(pcl_ctx *ctx, uintptr_t stream);
+
+/* ---- steps --------------------------------------------------------------------------------- */
+/* NewtonianKinematicsStep.run (physicl/newton.py:14-16): dr = v*dt; r += dr.
+ * With accel != 0: v += a*dt first (a from the ax/ay/az planes if present, else `a_uniform[3]`);
+ * that integrator is not in the reference (Object.a is never read). */
+int pcl_kinematics(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
+                   const float *a_uniform);
+/* nsteps back-to-back kinematics steps replayed from a CUDA graph (one launch per step). */
+int pcl_kinematics_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
+                         const float *a_uniform, uint32_t nsteps);
+
+/* ScatterIsotropicStep.__run_cl kernel + write-back (light.py:303-315, :325-331) and
+ * ScatterDeleteStep (light.py:239-249, :258-260).  Reads the dr planes the kinematics step left.
+ * `flags` (nullable, int32[n]) receives the reference's int result / NaN marker: 1 = scattered. */
+int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_scatter_params *sp,
+                const pcl_rng *rng, int32_t *flags, int64_t *tally_row);
+
+/* One whole photon timestep in one HBM round trip:
+ * kinematics (newton.py:14-16) -> scatter (light.py:303-315) -> escape sphere (new) ->
+ * sign + plane tallies (light.py:414-431, :385-399) accumulated into tally_row[PCL_TALLY_COLS].
+ * escape_r2 <= 0 disables the sphere; planes may be NULL.  tally_row must be zeroed by the caller
+ * (or use pcl_photon_steps). */
+int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
+                    const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                    const pcl_planes *planes, int64_t *tally_row);
+/* nsteps fused steps; rng->step is the first step index; tally_table is
+ * int64[nsteps][PCL_TALLY_COLS] in device memory, zeroed here. */
+int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
+                     const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                     const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps);
+
+/* ScatterSignMeasureStep.run / ScatterMeasureStep.run as stand-alone device tallies
+ * (light.py:414-431, :374-404).  Adds into tally_row[PCL_TALLY_COLS] (caller zeroes). */
+int pcl_tally(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_planes *planes,
+              int64_t *tally_row);
+
+/* Simulation.remove_obj for every retired photon (physicl/__init__.py:455-459): stable stream
+ * compaction of live slots of `src` into `dst` (dst planes must not alias src; dst->id required).
+ * n_live_dev: device uint64 receiving the live count. */
+int pcl_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_soa *dst,
+                uint64_t *n_live_dev);
+
+/* planck_phot_distribution (light.py:73-104): inverse-CDF draw on the reference's binned law.
+ * cdf: device float64[ncdf] (= bins-1 cumulative masses, light.py:88-93); grid energy of bin x
+ * is e_min + x*(e_max-e_min)/(bins-1) scaled by 1/E0 by the caller (e_lo, e_step are in E0 units).
+ * bin_out (nullable) gets x, or -1 where the reference falls off its loop and returns None. */
+int pcl_planck_sample(pcl_ctx *ctx, uintptr_t stream, uint64_t n, uint64_t id_base, uint64_t seed,
+                      const double *cdf, uint32_t ncdf, float e_lo, float e_step, float *e_out,
+                      int32_t *bin_out);
+
+/* All-pairs gravity (not in the reference; behind the Step API): for local bodies i in
+ * [0, n_local) a_i = G * sum_j m_j (r_j - r_i) / (|r_ij|^2 + eps2)^(3/2) over posm_all[0..n_total),
+ * float4 = (x, y, z, m).  posm_local are the i-bodies. Writes ax, ay, az. */
+int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
+                      const float *posm_all, uint64_t n_total, float G, float eps2, float *ax,
+                      float *ay, float *az, int accumulate);
+/* kick-drift for gravity bodies: v += a*dt; r += v*dt, and refresh posm (x,y,z,m). */
+int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx,
+                           float *vy, float *vz, const float *ax, const float *ay, const float *az,
+                           float dt);
+
+/* ---- host-buffer entry point (the reference's per-step marshalling, __init__.py:602-664) ---- */
+/* One fused photon step over HOST SoA planes: chunks are copied H2D, stepped and copied back D2H
+ * on rotating streams so PCIe and the kernel overlap.  Host planes should be pinned
+ * (pcl_host_register).  tally_row_host: int64[PCL_TALLY_COLS] written on return (synchronous). */
+int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                         const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                         int64_t *tally_row_host, uint64_t chunk);
+int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes);
+int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
+
+/* ---- roofline denominators measured on the box --------------------------------------------- */
+/* FFMA-only and copy micro-kernels; results in TFLOP/s (2 flop per FMA) and GB/s (read+write). */
+int pcl_measure_fp32_peak(pcl_ctx *ctx, double *tflops);
+int pcl_measure_copy_peak(pcl_ctx *ctx, uint64_t bytes, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYSICL_B200_H */

@@ -1,0 +1,124 @@
+// Host-buffer entry point: one fused photon step over particle planes that live in HOST memory.
+//
+// This is the shape of the reference's own per-step marshalling (CLProgram.run,
+// physicl/__init__.py:602-664: cl_array.to_device per input :614, launch :656, .get() per output
+// :659-662), restated for PCIe Gen5 + B200: the shard is cut into chunks, and chunk c's H2D copies,
+// its kernel and its D2H copies are queued on stream c % PIPE_SLOTS, so the two copy engines and
+// the SMs all stay busy.  Bytes over PCIe per photon-step: 24 B up (r, v) + 24 B down (+4 B e up).
+#include "pcl_common.cuh"
+
+int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, const pcl_scatter_params *sp,
+                         const pcl_rng *rng, float escape_r2, const pcl_planes *planes, int64_t *tally_row);
+
+#define PIPE_SLOTS 3
+#define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
+
+struct pcl_hostpipe {
+    uint64_t chunk;
+    cudaStream_t stream[PIPE_SLOTS];
+    float *buf[PIPE_SLOTS][12];
+    int64_t *tally_dev;
+    int64_t *tally_pinned;
+};
+
+void pcl_hostpipe_destroy(pcl_ctx *ctx) {
+    pcl_hostpipe *hp = ctx->pipe;
+    if (!hp) return;
+    for (int s = 0; s < PIPE_SLOTS; ++s) {
+        if (hp->stream[s]) cudaStreamDestroy(hp->stream[s]);
+        for (int q = 0; q < 12; ++q)
+            if (hp->buf[s][q]) cudaFree(hp->buf[s][q]);
+    }
+    if (hp->tally_dev) cudaFree(hp->tally_dev);
+    if (hp->tally_pinned) cudaFreeHost(hp->tally_pinned);
+    free(hp);
+    ctx->pipe = nullptr;
+}
+
+static int pipe_prepare(pcl_ctx *ctx, uint64_t chunk) {
+    if (ctx->pipe && ctx->pipe->chunk == chunk) return 0;
+    pcl_hostpipe_destroy(ctx);
+    pcl_hostpipe *hp = (pcl_hostpipe *)calloc(1, sizeof(pcl_hostpipe));
+    PCL_REQUIRE(ctx, hp != nullptr, "out of host memory");
+    ctx->pipe = hp;
+    hp->chunk = chunk;
+    for (int s = 0; s < PIPE_SLOTS; ++s) {
+        PCL_CUDA(ctx, cudaStreamCreateWithFlags(&hp->stream[s], cudaStreamNonBlocking));
+        for (int q = 0; q < 12; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->buf[s][q], chunk * sizeof(float)));
+    }
+    PCL_CUDA(ctx, cudaMalloc(&hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t)));
+    PCL_CUDA(ctx, cudaMallocHost(&hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t)));
+    return 0;
+}
+
+extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                                    const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                                    int64_t *tally_row_host, uint64_t chunk) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, host && sp && rng && tally_row_host, "null argument");
+    PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz, "r and v planes are required");
+    if (chunk == 0) chunk = 1u << 20;
+    chunk = (chunk + 3) & ~(uint64_t)3;
+    int rc = pipe_prepare(ctx, chunk);
+    if (rc) return rc;
+    pcl_hostpipe *hp = ctx->pipe;
+    const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH;
+    if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
+    const bool inj = rng->u_rand != nullptr;
+    PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
+    PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[0]));
+    uint64_t nchunks = (host->n + chunk - 1) / chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % PIPE_SLOTS);
+        cudaStream_t st = hp->stream[s];
+        const uint64_t off = c * chunk;
+        const uint64_t m = (host->n - off < chunk) ? host->n - off : chunk;
+        const size_t bytes = m * sizeof(float);
+        float **b = hp->buf[s];
+        const float *src[6] = {host->x, host->y, host->z, host->vx, host->vy, host->vz};
+        for (int q = 0; q < 6; ++q)
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[q], src[q] + off, bytes, cudaMemcpyHostToDevice, st));
+        pcl_soa d;
+        memset(&d, 0, sizeof(d));
+        d.n = m;
+        d.x = b[0]; d.y = b[1]; d.z = b[2]; d.vx = b[3]; d.vy = b[4]; d.vz = b[5];
+        d.id_base = host->id_base + (host->id ? 0 : off);
+        if (wave) {
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[6], host->e + off, bytes, cudaMemcpyHostToDevice, st));
+            d.e = b[6];
+        }
+        if (host->id) {
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[7], host->id + off, bytes, cudaMemcpyHostToDevice, st));
+            d.id = (uint32_t *)b[7];
+        }
+        if (host->nscat) {
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[8], host->nscat + off, bytes, cudaMemcpyHostToDevice, st));
+            d.nscat = (uint32_t *)b[8];
+        }
+        pcl_rng r = *rng;
+        if (inj) {
+            const bool del = sp->mode & PCL_SCATTER_DELETE;
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[11], rng->u_rand + off, bytes, cudaMemcpyHostToDevice, st));
+            r.u_rand = b[11];
+            r.u_theta = r.u_phi = nullptr;
+            if (!del) {
+                PCL_REQUIRE(ctx, rng->u_theta && rng->u_phi, "injected uniforms need u_theta and u_phi");
+                PCL_CUDA(ctx, cudaMemcpyAsync(b[9], rng->u_theta + off, bytes, cudaMemcpyHostToDevice, st));
+                PCL_CUDA(ctx, cudaMemcpyAsync(b[10], rng->u_phi + off, bytes, cudaMemcpyHostToDevice, st));
+                r.u_theta = b[9];
+                r.u_phi = b[10];
+            }
+        }
+        rc = pcl_photon_step_impl(ctx, st, &d, dt, sp, &r, escape_r2, planes, hp->tally_dev);
+        if (rc) return rc;
+        float *dst[6] = {host->x, host->y, host->z, host->vx, host->vy, host->vz};
+        for (int q = 0; q < 6; ++q)
+            PCL_CUDA(ctx, cudaMemcpyAsync(dst[q] + off, b[q], bytes, cudaMemcpyDeviceToHost, st));
+        if (host->nscat)
+            PCL_CUDA(ctx, cudaMemcpyAsync(host->nscat + off, b[8], bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
+    PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
+    return 0;
+}

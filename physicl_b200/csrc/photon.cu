@@ -1,0 +1,511 @@
+// Photon steps: scatter (isotropic / wavelength-dependent / delete), the fused whole-timestep
+// kernel, and the integer tallies of the reference's measure steps.
+//
+// Reference semantics restated (physicl/light.py):
+//   :305  norm  = sqrt(d0^2 + d1^2 + d2^2)                (dr left by newton.py:15)
+//   :306  pcoll = A * n * norm [ * ((h*c)/E)^-4 ]          (:300-301)
+//   :307  if (pcoll >= rand)                               rand ~ U[0,1)      (:285)
+//   :309-311  v = c*sin(rtheta)*cos(rphi), c*sin(rtheta)*sin(rphi), c*cos(rtheta)
+//             rtheta = U*2*pi, rphi = U*pi                 (:285)
+//   :146-158 / :239-249  delete flavour: result = pcoll >= rand, flagged photons are removed
+//   :414-431  sign tally: N, #(v_x>0), #(v_y>0), #(v_z>0)
+//   :385-399  plane tally: loc in the closed interval between r-dr and r
+//
+// FP32 re-expression: host folds k = A*n (and (E0/(h c))^4 for the wavelength law) in float64 and
+// photons carry e = E/E0, so pcoll = (k*norm)*(e^2)^2 stays in binary32 range for the reference's
+// own Rayleigh constants (A ~ 4e-56 m^6, E ~ 1e-19 J).
+//
+// Fused step traffic per live photon-step: read r,v 24 B + write r 12 B + write v 12 B for the
+// 16-byte groups that contain a scattered photon (+4 B e, +4 B id, +8 B nscat when present).
+#include "pcl_common.cuh"
+
+struct StepK {
+    float dt;
+    float k;
+    float c;
+    float r2_escape;  // <= 0: no sphere
+    uint32_t seed_lo, seed_hi;
+    uint32_t step;
+    uint32_t nplanes;
+    uint32_t axis[PCL_MAX_PLANES];
+    float loc[PCL_MAX_PLANES];
+    const float *u_theta, *u_phi, *u_rand;
+};
+
+enum { F_SCATTERED = 1, F_ABSORBED = 2, F_ESCAPED = 4 };
+
+// tally columns held in registers per thread
+enum { C_ALIVE, C_XP, C_YP, C_ZP, C_SCAT, C_ABS, C_ESC, C_LIVEIN, C_PLANE0, C_N = C_PLANE0 + PCL_MAX_PLANES };
+
+__device__ __forceinline__ float pcl_norm3(float dx, float dy, float dz) {
+    float s = dx * dx;
+    s = fmaf(dy, dy, s);
+    s = fmaf(dz, dz, s);
+    return sqrtf(s);
+}
+
+// The scatter decision and the new direction for one photon.  dx,dy,dz is this step's dr.
+template <bool WAVE, bool DEL>
+__device__ __forceinline__ uint32_t pcl_scatter_one(float dx, float dy, float dz, float e,
+                                                    float ut, float up, float ur, float k, float c,
+                                                    float &vx, float &vy, float &vz) {
+    float norm = pcl_norm3(dx, dy, dz);
+    float pcoll = k * norm;
+    if (WAVE) {
+        float e2 = e * e;
+        float e4 = e2 * e2;
+        pcoll = pcoll * e4;
+    }
+    if (!(pcoll >= ur)) return 0u;
+    if (DEL) return F_SCATTERED | F_ABSORBED;
+    float st, ct, sp, cp;
+    pcl_sincospi(ut + ut, st, ct);  // theta = 2*pi*u
+    pcl_sincospi(up, sp, cp);       // phi   =   pi*u
+    float cs = c * st;
+    vx = cs * cp;
+    vy = cs * sp;
+    vz = c * ct;
+    return F_SCATTERED;
+}
+
+__device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut, float &up, float &ur) {
+    uint4 r = pcl_philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), K.step, 0u),
+                                make_uint2(K.seed_lo, K.seed_hi));
+    ut = pcl_u01(r.x);
+    up = pcl_u01(r.y);
+    ur = pcl_u01(r.z);
+}
+
+template <int NC>
+__device__ __forceinline__ void pcl_tally_one(const StepK &K, float x, float y, float z, float dx,
+                                              float dy, float dz, float vx, float vy, float vz,
+                                              uint32_t (&cnt)[NC]) {
+    cnt[C_ALIVE] += 1u;
+    cnt[C_XP] += (vx > 0.f) ? 1u : 0u;
+    cnt[C_YP] += (vy > 0.f) ? 1u : 0u;
+    cnt[C_ZP] += (vz > 0.f) ? 1u : 0u;
+#pragma unroll
+    for (int q = 0; q < NC - (int)C_PLANE0; ++q) {
+        if ((uint32_t)q < K.nplanes) {
+            uint32_t ax = K.axis[q];
+            float r = ax == 0 ? x : (ax == 1 ? y : z);
+            float d = ax == 0 ? dx : (ax == 1 ? dy : dz);
+            float prev = r - d;  // light.py:386: obj.r[0] - obj.dr[0], evaluated after r += dr
+            float loc = K.loc[q];
+            bool hit = (prev <= loc && loc <= r) || (prev >= loc && loc >= r);
+            cnt[C_PLANE0 + q] += hit ? 1u : 0u;
+        }
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ void pcl_flush_tally(const uint32_t (&cnt)[NC], int64_t *row, uint32_t nplanes) {
+    __shared__ unsigned int s_acc[C_N];
+    if (threadIdx.x < C_N) s_acc[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        if (q < C_PLANE0 + (int)nplanes) {
+            unsigned int w = __reduce_add_sync(0xffffffffu, cnt[q]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_acc[q], w);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < C_N && s_acc[threadIdx.x]) {
+        // register column -> PCL_T_* column (identical numbering by construction)
+        atomicAdd((unsigned long long *)&row[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+    }
+}
+
+static_assert((int)C_ALIVE == (int)PCL_T_ALIVE && (int)C_XP == (int)PCL_T_XP && (int)C_ZP == (int)PCL_T_ZP &&
+                  (int)C_SCAT == (int)PCL_T_SCATTERED && (int)C_ABS == (int)PCL_T_ABSORBED &&
+                  (int)C_ESC == (int)PCL_T_ESCAPED && (int)C_LIVEIN == (int)PCL_T_LIVE_IN &&
+                  (int)C_PLANE0 == (int)PCL_T_PLANE0 && (int)C_N == (int)PCL_TALLY_COLS,
+              "register tally layout must match the ABI row layout");
+
+// ---------------------------------------------------------------------------------------------
+// Fused photon step, 4 photons per thread.
+// ---------------------------------------------------------------------------------------------
+template <bool WAVE, bool DEL, bool INJ, bool PL>
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row, uint64_t nvec) {
+    constexpr int NC = PL ? C_N : C_PLANE0;
+    uint32_t cnt[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    const float qnan = __int_as_float(0x7fc00000);
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; g < nvec; g += stride) {
+        const uint64_t i = g * 4;
+        float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
+        float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
+        float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (WAVE) e = pcl_ld4(p.e + i);
+        uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
+        const bool has_id = p.id != nullptr;
+        if (has_id) id = pcl_ld4u(p.id + i);
+        float4 ut4, up4, ur4;
+        if (INJ) {
+            ut4 = pcl_ld4(K.u_theta + i);
+            up4 = pcl_ld4(K.u_phi + i);
+            ur4 = pcl_ld4(K.u_rand + i);
+        }
+        uint32_t any_scat = 0u;
+        uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
+        if (p.nscat) nsc = pcl_ld4u(p.nscat + i);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            float xx = pcl_f4(x, l);
+            if (xx != xx) continue;  // retired slot
+            cnt[C_LIVEIN] += 1u;
+            float dx = pcl_f4(vx, l) * K.dt, dy = pcl_f4(vy, l) * K.dt, dz = pcl_f4(vz, l) * K.dt;
+            xx = xx + dx;
+            float yy = pcl_f4(y, l) + dy;
+            float zz = pcl_f4(z, l) + dz;
+            float ut, up, ur;
+            if (INJ) {
+                ut = pcl_f4(ut4, l);
+                up = pcl_f4(up4, l);
+                ur = pcl_f4(ur4, l);
+            } else {
+                uint64_t gid = p.id_base + (has_id ? (uint64_t)pcl_u4(id, l) : (i + (uint64_t)l));
+                pcl_draw(K, gid, ut, up, ur);
+            }
+            uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, pcl_f4(e, l), ut, up, ur, K.k, K.c,
+                                                    pcl_f4(vx, l), pcl_f4(vy, l), pcl_f4(vz, l));
+            if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
+                float r2 = xx * xx;
+                r2 = fmaf(yy, yy, r2);
+                r2 = fmaf(zz, zz, r2);
+                if (r2 >= K.r2_escape) f |= F_ESCAPED;
+            }
+            cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
+            cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
+            cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
+            if (!DEL && (f & F_SCATTERED)) {
+                any_scat = 1u;
+                pcl_u4(nsc, l) += 1u;
+            }
+            if (f & (F_ABSORBED | F_ESCAPED)) {
+                xx = qnan;
+            } else {
+                pcl_tally_one(K, xx, yy, zz, dx, dy, dz, pcl_f4(vx, l), pcl_f4(vy, l), pcl_f4(vz, l), cnt);
+            }
+            pcl_f4(x, l) = xx;
+            pcl_f4(y, l) = yy;
+            pcl_f4(z, l) = zz;
+        }
+        pcl_st4(p.x + i, x);
+        pcl_st4(p.y + i, y);
+        pcl_st4(p.z + i, z);
+        if (any_scat) {
+            pcl_st4(p.vx + i, vx);
+            pcl_st4(p.vy + i, vy);
+            pcl_st4(p.vz + i, vz);
+            if (p.nscat) pcl_st4u(p.nscat + i, nsc);
+        }
+    }
+    pcl_flush_tally(cnt, row, K.nplanes);
+}
+
+// scalar form: tails, unaligned views
+template <bool WAVE, bool DEL, bool INJ, bool PL>
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, uint64_t begin, uint64_t end) {
+    constexpr int NC = PL ? C_N : C_PLANE0;
+    uint32_t cnt[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    const float qnan = __int_as_float(0x7fc00000);
+    uint64_t i = begin + (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x;
+    if (i < end) {
+        float xx = p.x[i];
+        if (xx == xx) {
+            cnt[C_LIVEIN] += 1u;
+            float vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+            float dx = vx * K.dt, dy = vy * K.dt, dz = vz * K.dt;
+            xx = xx + dx;
+            float yy = p.y[i] + dy, zz = p.z[i] + dz;
+            float ut, up, ur;
+            if (INJ) {
+                ut = K.u_theta[i];
+                up = K.u_phi[i];
+                ur = K.u_rand[i];
+            } else {
+                uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
+                pcl_draw(K, gid, ut, up, ur);
+            }
+            float e = WAVE ? p.e[i] : 1.f;
+            uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz);
+            if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
+                float r2 = xx * xx;
+                r2 = fmaf(yy, yy, r2);
+                r2 = fmaf(zz, zz, r2);
+                if (r2 >= K.r2_escape) f |= F_ESCAPED;
+            }
+            cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
+            cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
+            cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
+            if (f & (F_ABSORBED | F_ESCAPED)) {
+                xx = qnan;
+            } else {
+                pcl_tally_one(K, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
+            }
+            p.x[i] = xx;
+            p.y[i] = yy;
+            p.z[i] = zz;
+            if (!DEL && (f & F_SCATTERED)) {
+                p.vx[i] = vx;
+                p.vy[i] = vy;
+                p.vz[i] = vz;
+                if (p.nscat) p.nscat[i] += 1u;
+            }
+        }
+    }
+    pcl_flush_tally(cnt, row, K.nplanes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone scatter: what CLProgram.run launches (physicl/__init__.py:656) plus the host
+// write-back loop (light.py:325-331).  Reads the dr planes written by the kinematics step.
+// ---------------------------------------------------------------------------------------------
+template <bool WAVE, bool DEL, bool INJ>
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
+    uint32_t cnt[C_PLANE0];
+#pragma unroll
+    for (int q = 0; q < C_PLANE0; ++q) cnt[q] = 0u;
+    const float qnan = __int_as_float(0x7fc00000);
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n; i += stride) {
+        float xx = p.x[i];
+        int32_t flag = 0;
+        if (xx == xx) {
+            cnt[C_LIVEIN] += 1u;
+            float ut, up, ur;
+            if (INJ) {
+                ut = K.u_theta[i];
+                up = K.u_phi[i];
+                ur = K.u_rand[i];
+            } else {
+                uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
+                pcl_draw(K, gid, ut, up, ur);
+            }
+            float vx = 0.f, vy = 0.f, vz = 0.f;
+            float e = WAVE ? p.e[i] : 1.f;
+            uint32_t f = pcl_scatter_one<WAVE, DEL>(p.dx[i], p.dy[i], p.dz[i], e, ut, up, ur, K.k, K.c, vx, vy, vz);
+            if (f & F_SCATTERED) {
+                flag = 1;
+                cnt[C_SCAT] += 1u;
+                if (DEL) {
+                    cnt[C_ABS] += 1u;
+                    p.x[i] = qnan;
+                } else {
+                    p.vx[i] = vx;
+                    p.vy[i] = vy;
+                    p.vz[i] = vz;
+                    if (p.nscat) p.nscat[i] += 1u;
+                }
+            }
+            if (!(f & F_ABSORBED)) cnt[C_ALIVE] += 1u;
+        }
+        if (flags) flags[i] = flag;
+    }
+    if (row) pcl_flush_tally(cnt, row, 0u);
+}
+
+// Stand-alone tallies (ScatterSignMeasureStep / ScatterMeasureStep).
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_tally(pcl_soa p, StepK K, int64_t *row, uint64_t n) {
+    uint32_t cnt[C_N];
+#pragma unroll
+    for (int q = 0; q < C_N; ++q) cnt[q] = 0u;
+    const bool has_dr = p.dx != nullptr;
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n; i += stride) {
+        float xx = p.x[i];
+        if (xx != xx) continue;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (has_dr) {
+            dx = p.dx[i];
+            dy = p.dy[i];
+            dz = p.dz[i];
+        }
+        pcl_tally_one(K, xx, p.y[i], p.z[i], dx, dy, dz, p.vx[i], p.vy[i], p.vz[i], cnt);
+    }
+    pcl_flush_tally(cnt, row, K.nplanes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *sp, const pcl_rng *rng,
+                      float escape_r2, const pcl_planes *planes) {
+    memset(&K, 0, sizeof(K));
+    K.dt = dt;
+    if (sp) {
+        K.k = sp->k;
+        K.c = sp->c;
+    }
+    K.r2_escape = escape_r2;
+    if (rng) {
+        K.seed_lo = (uint32_t)rng->seed;
+        K.seed_hi = (uint32_t)(rng->seed >> 32);
+        K.step = rng->step;
+        K.u_theta = rng->u_theta;
+        K.u_phi = rng->u_phi;
+        K.u_rand = rng->u_rand;
+        if (rng->u_rand) {
+            bool del = sp && (sp->mode & PCL_SCATTER_DELETE);
+            PCL_REQUIRE(ctx, del || (rng->u_theta && rng->u_phi),
+                        "injected uniforms need u_theta and u_phi as well as u_rand");
+            if (del) {  // the delete kernel only consumes rand (light.py:235)
+                if (!K.u_theta) K.u_theta = rng->u_rand;
+                if (!K.u_phi) K.u_phi = rng->u_rand;
+            }
+        }
+    }
+    if (planes) {
+        PCL_REQUIRE(ctx, planes->count <= PCL_MAX_PLANES, "too many planes");
+        K.nplanes = planes->count;
+        for (uint32_t q = 0; q < planes->count; ++q) {
+            PCL_REQUIRE(ctx, planes->axis[q] < 3, "plane axis must be 0, 1 or 2");
+            K.axis[q] = planes->axis[q];
+            K.loc[q] = planes->loc[q];
+        }
+    }
+    return 0;
+}
+
+template <bool WAVE, bool DEL, bool INJ, bool PL>
+static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const StepK &K, int64_t *row) {
+    bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) && pcl_aligned16(p.vx) &&
+                   pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
+                   pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
+                   pcl_aligned16(K.u_rand);
+    uint64_t nvec = aligned ? p.n / 4 : 0;
+    if (nvec) {
+        unsigned grid = pcl_stream_grid(ctx, nvec, PCL_BLOCK, 8);
+        pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, nvec);
+        PCL_LAUNCHED(ctx);
+    }
+    uint64_t begin = nvec * 4;
+    if (begin < p.n) {
+        unsigned grid = (unsigned)((p.n - begin + PCL_BLOCK - 1) / PCL_BLOCK);
+        pcl_k_photon_step_tail<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, begin, p.n);
+        PCL_LAUNCHED(ctx);
+    }
+    return 0;
+}
+
+template <bool WAVE, bool DEL, bool INJ>
+static int launch_photon(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const StepK &K, int64_t *row) {
+    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, K, row)
+                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, K, row);
+}
+
+static int photon_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const StepK &K, uint32_t mode,
+                           int64_t *row) {
+    const bool wave = mode & PCL_SCATTER_WAVELENGTH, del = mode & PCL_SCATTER_DELETE, inj = K.u_rand != nullptr;
+    switch ((wave ? 4 : 0) | (del ? 2 : 0) | (inj ? 1 : 0)) {
+        case 0: return launch_photon<false, false, false>(ctx, st, *p, K, row);
+        case 1: return launch_photon<false, false, true>(ctx, st, *p, K, row);
+        case 2: return launch_photon<false, true, false>(ctx, st, *p, K, row);
+        case 3: return launch_photon<false, true, true>(ctx, st, *p, K, row);
+        case 4: return launch_photon<true, false, false>(ctx, st, *p, K, row);
+        case 5: return launch_photon<true, false, true>(ctx, st, *p, K, row);
+        case 6: return launch_photon<true, true, false>(ctx, st, *p, K, row);
+        default: return launch_photon<true, true, true>(ctx, st, *p, K, row);
+    }
+}
+
+static int check_photon_view(pcl_ctx *ctx, const pcl_soa *p, const pcl_scatter_params *sp) {
+    PCL_REQUIRE(ctx, p != nullptr && sp != nullptr, "null argument");
+    PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
+    PCL_REQUIRE(ctx, p->n < (1ull << 32), "a shard holds fewer than 2^32 slots");
+    if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
+    return 0;
+}
+
+int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, const pcl_scatter_params *sp,
+                         const pcl_rng *rng, float escape_r2, const pcl_planes *planes, int64_t *tally_row) {
+    int rc = check_photon_view(ctx, p, sp);
+    if (rc) return rc;
+    PCL_REQUIRE(ctx, tally_row != nullptr, "tally_row is required");
+    if (p->n == 0) return 0;
+    StepK K;
+    rc = fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
+    if (rc) return rc;
+    return photon_dispatch(ctx, st, p, K, sp->mode, tally_row);
+}
+
+extern "C" int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
+                               const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                               const pcl_planes *planes, int64_t *tally_row) {
+    PCL_ENTER(ctx);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, dt, sp, rng, escape_r2, planes, tally_row);
+}
+
+extern "C" int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
+                                const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                                const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, rng != nullptr, "rng is required");
+    PCL_REQUIRE(ctx, rng->u_rand == nullptr, "multi-step runs draw from Philox; injected uniforms are per step");
+    PCL_REQUIRE(ctx, tally_table != nullptr, "tally_table is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
+    pcl_rng r = *rng;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        r.step = rng->step + s;
+        int rc = pcl_photon_step_impl(ctx, st, p, dt, sp, &r, escape_r2, planes,
+                                      tally_table + (size_t)s * PCL_TALLY_COLS);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_scatter_params *sp,
+                           const pcl_rng *rng, int32_t *flags, int64_t *tally_row) {
+    PCL_ENTER(ctx);
+    int rc = check_photon_view(ctx, p, sp);
+    if (rc) return rc;
+    PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "stand-alone scatter reads the dr planes");
+    if (p->n == 0) return 0;
+    StepK K;
+    rc = fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
+    const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH, del = sp->mode & PCL_SCATTER_DELETE, inj = K.u_rand != nullptr;
+#define PCL_SC(W, D, I) pcl_k_scatter<W, D, I><<<grid, PCL_BLOCK, 0, st>>>(*p, K, flags, tally_row, p->n)
+    switch ((wave ? 4 : 0) | (del ? 2 : 0) | (inj ? 1 : 0)) {
+        case 0: PCL_SC(false, false, false); break;
+        case 1: PCL_SC(false, false, true); break;
+        case 2: PCL_SC(false, true, false); break;
+        case 3: PCL_SC(false, true, true); break;
+        case 4: PCL_SC(true, false, false); break;
+        case 5: PCL_SC(true, false, true); break;
+        case 6: PCL_SC(true, true, false); break;
+        default: PCL_SC(true, true, true); break;
+    }
+#undef PCL_SC
+    PCL_LAUNCHED(ctx);
+    return 0;
+}
+
+extern "C" int pcl_tally(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_planes *planes,
+                         int64_t *tally_row) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, p != nullptr && tally_row != nullptr, "null argument");
+    PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
+    if (planes && planes->count) PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "plane tallies read the dr planes");
+    if (p->n == 0) return 0;
+    StepK K;
+    int rc = fill_stepk(ctx, K, 0.f, nullptr, nullptr, 0.f, planes);
+    if (rc) return rc;
+    unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
+    pcl_k_tally<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(*p, K, tally_row, p->n);
+    PCL_LAUNCHED(ctx);
+    return 0;
+}
