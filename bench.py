@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""Benchmark of the per-particle step hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Default workload (BASELINE.json configs[1]): isotropic photon scattering in a uniform sphere,
+16 Mi photons per GPU, A = n = 1e-3, dt = 1e-3 (pcoll ~ 0.2998 per step, reference
+test/test_light.py:32-34), escape sphere R = 3 mean free paths, per-step sign tallies and the
+escape-time histogram.  One "step" = one timestep of the whole pipeline (kinematics + scatter +
+escape + tallies) over every live photon.  metric = particle-steps/s, whole job.
+
+  value      state resident in HBM, stepped through Simulation.run_steps (public API); CUDA events
+  e2e        same step through the host-buffer C-ABI entry point (pcl_photon_step_host): particle
+             planes start and end in pinned HOST memory every step (H2D + kernel + D2H timed)
+  roofline   fused photon-step kernel: algorithmic bytes / launch time
+  cpu_baseline / --impl reference
+             the reference's law in float64 (oracle/c/oracle.c: orc_photon_step_f64, OpenMP over
+             all host cores) on a bounded sample of the same workload
+
+Other workloads (--workload): kinematics_1m (configs[0], CUDA-graph stepped), kinematics_64m,
+wavelength_64m (configs[2]), gravity_256k (configs[3]); same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C_LIGHT = 299792458.0
+PHOTONS_PER_GPU = 16 * 2 ** 20
+A_N = 1e-3 * 1e-3  # A * n of reference test/test_light.py:34
+DT = 1e-3
+R_ESCAPE = 3.0 / A_N  # three mean free paths
+SEED = 2024
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def init_dist(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    if world != n_gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (n_gpus, world, n_gpus))
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's law in float64, OpenMP over all host cores (oracle port)
+# ---------------------------------------------------------------------------------------------
+def cpu_photon_sphere(n, steps, warmup):
+    import oracle
+
+    st = {k: np.zeros(n) for k in ("x", "y", "z", "vx", "vy", "vz")}
+    st["vx"][:] = C_LIGHT
+    for s in range(warmup):
+        oracle.photon_step_f64(st, DT, 1e-3, 1e-3, 0.0, C_LIGHT, 0, SEED, s, R_ESCAPE ** 2)
+    live = 0
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + steps):
+        row = oracle.photon_step_f64(st, DT, 1e-3, 1e-3, 0.0, C_LIGHT, 0, SEED, s, R_ESCAPE ** 2)
+        live += int(row[oracle.T_LIVE_IN])
+    dt = time.perf_counter() - t0
+    return live / dt, dt, oracle.num_threads()
+
+
+def cpu_baseline_block(budget_s=15.0):
+    """Bounded sample: 2 Mi photons, as many steps as fit ~budget_s (at least 3)."""
+    n = 2 * 2 ** 20
+    rate, dt, cores = cpu_photon_sphere(n, 2, 1)
+    steps = int(max(3, min(40, budget_s / max(dt / 2, 1e-3))))
+    rate, dt, cores = cpu_photon_sphere(n, steps, 1)
+    return {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d photons x %d steps of the photon_sphere workload, float64 reference law "
+                      "(oracle/c/oracle.c orc_photon_step_f64, OpenMP), %.1f s" % (n, steps, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 4 * 2 ** 20
+    rate, dt, cores = cpu_photon_sphere(n, args.steps, args.warmup)
+    out = {
+        "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "photon_sphere_16m", "photons_per_step_sample": n,
+                   "note": "reference law on host cores; pyopencl/pocl are not installable here, so this is the C/OpenMP "
+                           "port of the reference kernels + kinematics (oracle/), the closest stand-in for OpenCL-on-CPU"},
+        "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d photons x %d steps" % (n, args.steps)},
+        "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def photon_sim(n, rank, local, wavelength=False):
+    import physicl_b200 as phys
+    import physicl_b200.light
+    import physicl_b200.newton
+
+    sim = phys.Simulation(cl_on=True, device=local, seed=SEED, exit=lambda s: False)
+    r = np.zeros((3, n), np.float32)
+    v = np.zeros((3, n), np.float32)
+    v[0] = C_LIGHT
+    sim.add_particles(r, v, E=None, id_base=rank * n)
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(DT)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+    esc = phys.light.EscapeSphereStep(R_ESCAPE)
+    sim.add_step(3, esc)
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    sim.add_step(4, sign)
+    return sim, esc, sign
+
+
+def bench_photon_sphere(args, rank, world, local):
+    import torch
+
+    from physicl_b200 import _capi
+
+    n = PHOTONS_PER_GPU
+    sim, esc, sign = photon_sim(n, rank, local)
+    ctx = sim.cl_ctx
+    sim.run_steps(args.warmup)
+    store = sim.store
+    row0 = store.current_row + 1
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        sim.run_steps(args.steps)
+        ev1.record()
+        barrier_sync(world)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world)
+    launches = ctx.launches - launches0
+    rows = np.array([store.read_row(r) for r in range(row0, store.current_row + 1)])
+    fused = rows[rows[:, _capi.T_LIVE_IN] > 0]
+    live = float(fused[:, _capi.T_LIVE_IN].sum())
+    scat = float(fused[:, _capi.T_SCATTERED].sum())
+    live_all = sum_over_ranks(live, world)
+    value = live_all / (ms * 1e-3)
+    alg_bytes = 36.0 * live + 12.0 * scat  # (36 + 12 f) B per photon-step
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    hist = esc.escaped
+
+    # ---- e2e: host buffers in, host buffers out, every step ---------------------------------
+    e2e = None
+    try:
+        host = {k: torch.zeros(n, dtype=torch.float32).pin_memory() for k in ("x", "y", "z", "vx", "vy", "vz")}
+        host["vx"].fill_(C_LIGHT)
+        soa = _capi.Soa()
+        soa.n = n
+        for k, t in host.items():
+            setattr(soa, k, t.data_ptr())
+        soa.id_base = rank * n
+        sp = _capi.ScatterParams(k=A_N, c=C_LIGHT, mode=0)
+        pl = _capi.make_planes([])
+        row = np.zeros(_capi.TALLY_COLS, np.int64)
+        k_e2e = max(3, min(args.steps, 20))
+
+        def host_step(s):
+            rg = _capi.Rng(seed=SEED, step=s)
+            ctx.call("pcl_photon_step_host", C.byref(soa), C.c_float(DT), C.byref(sp), C.byref(rg), C.c_float(R_ESCAPE ** 2),
+                     C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(1 << 20))
+            return int(row[_capi.T_LIVE_IN])
+
+        for s in range(3):
+            host_step(s)
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        live_e = 0
+        for s in range(3, 3 + k_e2e):
+            live_e += host_step(s)
+        barrier_sync(world)
+        wall = max_over_ranks(time.perf_counter() - t0, world)
+        e2e = {"value": sum_over_ranks(float(live_e), world) / wall, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 8 * _capi.TALLY_COLS, "steps": k_e2e,
+               "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
+               "path": "pcl_photon_step_host: pinned host SoA planes -> chunked H2D -> fused kernel -> D2H"}
+    except Exception as e:  # report, never hide
+        e2e = {"value": None, "unit": "particle-steps/s", "error": repr(e)}
+
+    cpu = cpu_baseline_block() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    out = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "photon_sphere_16m", "photons_per_gpu": n, "A": 1e-3, "n": 1e-3, "dt": DT,
+                   "escape_radius": R_ESCAPE, "seed": SEED, "rng": "philox4x32-10 in-kernel",
+                   "pipeline": "kinematics+scatter+escape+sign tally fused, 1 launch/step, compaction check every 16 steps",
+                   "l2": "state 384 MiB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)",
+                   "live_fraction_mean": live / (n * max(len(fused), 1)), "scattered_fraction": scat / max(live, 1),
+                   "escaped_in_window": int(hist[-args.steps:].sum()) if len(hist) else 0},
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "pcl_k_photon_step<0,0,0,0>",
+                     "algorithmic_bytes": "(36 + 12 f) B per live photon-step, f = scattered fraction (SURVEY.md 8d)",
+                     "per_rank": True},
+        "clocks": clocks.summary(),
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    return out
+
+
+def bench_kinematics(args, rank, world, local, n, accel, graph):
+    import torch
+
+    from physicl_b200 import _capi
+    from physicl_b200.store import DeviceParticleStore
+
+    ctx = _capi.Context(local)
+    rng = np.random.default_rng(1234 + rank)
+    st = DeviceParticleStore(ctx)
+    r = rng.uniform(-1e3, 1e3, (3, n)).astype(np.float32)
+    v = rng.normal(0, 10, (3, n)).astype(np.float32)
+    a = np.zeros((3, n), np.float32)
+    a[2] = -9.81
+    g = st.add_group("object", r, v, a=a if accel else None, id_base=rank * n)
+    g.ensure("dx", "dy", "dz")
+    soa = g.soa()
+    steps, chunk = args.steps, 50
+    def run(k):
+        if graph:
+            done = 0
+            while done < k:
+                m = min(chunk, k - done)
+                ctx.call("pcl_kinematics_steps", st.stream(), C.byref(soa), C.c_float(DT), int(accel), None, C.c_uint32(m))
+                done += m
+        else:
+            for _ in range(k):
+                ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(DT), int(accel), None)
+    run(max(args.warmup, chunk if graph else args.warmup))
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        run(steps)
+        ev1.record()
+        barrier_sync(world)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world)
+    bpp = 72.0 if accel else 48.0
+    peak, peak_src = measured_peaks()
+    achieved = bpp * n * steps / (ms * 1e-3) / 1e9
+    return {
+        "metric": "particle-steps/s", "value": n * world * steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "particles_per_gpu": n, "law": "v+=a dt; dr=v dt; r+=dr" if accel else "dr=v dt; r+=dr",
+                   "cuda_graph": bool(graph),
+                   "l2": "state %d MB per GPU %s" % (n * (48 if accel else 36) // 10 ** 6,
+                                                      "fits the 126 MB L2: HBM fraction is optimistic" if n * 48 < 120e6 else "> L2")},
+        "e2e": None, "gpu_launches": int(ctx.launches - l0),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "pcl_k_kinematics", "algorithmic_bytes": "%d B per particle-step" % bpp},
+        "clocks": clocks.summary(),
+    }
+
+
+def bench_gravity(args, rank, world, local):
+    import torch
+
+    import physicl_b200 as phys
+    import physicl_b200.newton
+
+    n_total = 262144
+    rng = np.random.default_rng(7)
+    # Plummer sphere, G = M = 1
+    m_r = rng.uniform(0, 1, n_total)
+    rad = 1.0 / np.sqrt(np.maximum(m_r ** (-2.0 / 3.0) - 1.0, 1e-12))
+    d = rng.normal(size=(3, n_total))
+    pos = rad * d / np.linalg.norm(d, axis=0)
+    vel = rng.normal(0, 0.3, (3, n_total))
+    sim = phys.Simulation(cl_on=True, device=local, shard=world > 1, exit=lambda s: False)
+    sim.add_particles(pos, vel, kind="object")
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+    sim.add_step(1, phys.newton.NewtonianGravityStep(G=1.0, eps2=1e-4, masses=np.full(n_total, 1.0 / n_total, np.float32)))
+    sim.run_steps(max(1, min(args.warmup, 3)))
+    ctx = sim.cl_ctx
+    fp32_peak = ctx.fp32_peak_tflops()
+    l0 = ctx.launches
+    steps = args.steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        sim.run_steps(steps)
+        ev1.record()
+        barrier_sync(world)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world)
+    inter = float(n_total) * n_total * steps
+    tf = 20.0 * inter / world / (ms * 1e-3) / 1e12  # per GPU
+    return {
+        "metric": "particle-steps/s", "value": n_total * steps / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "gravity_256k", "bodies": n_total, "eps2": 1e-4, "dt": 1e-3, "interactions_per_s": inter / (ms * 1e-3)},
+        "e2e": None, "gpu_launches": int(ctx.launches - l0),
+        "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
+                     "peak_source": "FFMA-only micro-kernel measured in this run (pcl_measure_fp32_peak)",
+                     "kernel": "pcl_k_gravity<4>", "algorithmic_flops": "20 FLOP per pairwise interaction", "per_rank": True},
+        "clocks": clocks.summary(),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="photon_sphere_16m",
+                    choices=["photon_sphere_16m", "kinematics_1m", "kinematics_64m", "kinematics_ref_64m", "gravity_256k"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: physicl_b200 has no CPU path (use --impl reference for the CPU arm)")
+    rank, world, local = init_dist(args.gpus)
+    if args.workload == "photon_sphere_16m":
+        out = bench_photon_sphere(args, rank, world, local)
+    elif args.workload == "kinematics_1m":
+        out = bench_kinematics(args, rank, world, local, 1_000_000, True, True)
+    elif args.workload == "kinematics_64m":
+        out = bench_kinematics(args, rank, world, local, 64 * 2 ** 20, True, False)
+    elif args.workload == "kinematics_ref_64m":
+        out = bench_kinematics(args, rank, world, local, 64 * 2 ** 20, False, False)
+    else:
+        out = bench_gravity(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,11 @@ int pcl_kinematics_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float
 int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_scatter_params *sp,
                 const pcl_rng *rng, int32_t *flags, int64_t *tally_row);
 
+/* Escape sphere as a stand-alone step (not in the reference: Simulation.bounds is stored and never
+ * read, physicl/__init__.py:412): photons with |r|^2 >= r2 retire.  Adds ESCAPED / ALIVE / LIVE_IN
+ * into tally_row (nullable). */
+int pcl_escape(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float r2, int64_t *tally_row);
+
 /* One whole photon timestep in one HBM round trip:
  * kinematics (newton.py:14-16) -> scatter (light.py:303-315) -> escape sphere (new) ->
  * sign + plane tallies (light.py:414-431, :385-399) accumulated into tally_row[PCL_TALLY_COLS].
@@ -162,10 +167,11 @@ int pcl_planck_sample(pcl_ctx *ctx, uintptr_t stream, uint64_t n, uint64_t id_ba
 int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
                       const float *posm_all, uint64_t n_total, float G, float eps2, float *ax,
                       float *ay, float *az, int accumulate);
-/* kick-drift for gravity bodies: v += a*dt; r += v*dt, and refresh posm (x,y,z,m). */
+/* kick-drift for gravity bodies: v += a*dt; r += v*dt on the packed posm (x,y,z,m); x,y,z
+ * (nullable triple) are the store's SoA position planes, refreshed in the same pass. */
 int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx,
                            float *vy, float *vz, const float *ax, const float *ay, const float *az,
-                           float dt);
+                           float dt, float *x, float *y, float *z);
 
 /* ---- host-buffer entry point (the reference's per-step marshalling, __init__.py:602-664) ---- */
 /* One fused photon step over HOST SoA planes: chunks are copied H2D, stepped and copied back D2H

@@ -1,0 +1,430 @@
+"""physicl_b200: a B200 (sm_100a) backend behind PhysiCL's ``Simulation`` / ``Step`` API.
+
+Host-side mirror of ``physicl/__init__.py`` of the reference (bcwarner/physicl): same class names,
+same argument meaning, same error behaviour for the per-particle step path, so a user of the
+reference can ``import physicl_b200 as physicl``.  What differs is underneath: particle state is
+uploaded once into structure-of-arrays float32 planes in HBM (``store.DeviceParticleStore``) and
+every step is a hand-written CUDA kernel reached through a C ABI (``include/physicl_b200.h``).
+
+There is no CPU fallback: ``cl_on=True`` (the reference's "use the device" switch,
+physicl/__init__.py:413) needs the built library and a B200; device steps raise otherwise.
+``cl_on=False`` builds a host-only ``Simulation`` (time stepping, user steps, measure-step files).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import threading
+import time
+
+import numpy as np
+
+from .units import Measurement, MeasurementError  # noqa: F401
+
+__all__ = ["Measurement", "MeasurementError", "Step", "UpdateTimeStep", "MeasureStep", "Object", "Simulation",
+           "IndexException"]
+
+
+class IndexException(NameError):
+    """Raised by ``Simulation.add_step`` for a duplicate index.  The reference raises an undefined
+    name there (physicl/__init__.py:441), i.e. a ``NameError``; this class keeps both readings."""
+
+
+class Step:
+    """Plugin protocol of the reference (physicl/__init__.py:293-322): ``run(sim)`` once per
+    timestep, ``terminate(sim)`` once at the end.  ``uses_device`` marks steps that operate on the
+    HBM-resident store; everything else is treated as a host step that reads ``sim.objects``."""
+
+    uses_device = False
+
+    def __init__(self):
+        pass
+
+    def run(self, sim):
+        pass
+
+    def terminate(self, sim):
+        pass
+
+
+class UpdateTimeStep(Step):
+    """physicl/__init__.py:324-343: ``dt = fn(sim); t += dt; ts.append(copy of t)``."""
+
+    touches_objects = False
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def run(self, sim):
+        sim.dt = self.fn(sim)
+        sim.t += sim.dt
+        sim.ts.append(copy.deepcopy(sim.t))
+
+
+class MeasureStep(Step):
+    """physicl/__init__.py:345-378: accumulates ``data`` and writes comma-separated rows on
+    ``terminate`` when an output file name was given."""
+
+    def __init__(self, out_fn=None):
+        self.out_fn = out_fn
+        self.data = []
+
+    def run(self, sim):
+        pass
+
+    def terminate(self, sim):
+        if self.out_fn is None:
+            return
+        rows = self.data.values() if isinstance(self.data, dict) else self.data
+        with open(self.out_fn, "w") as f:
+            for row in rows:
+                f.write(", ".join(str(i) for i in list(row)) + "\n")
+
+
+class Object:
+    """physicl/__init__.py:381-396: position ``r``, last displacement ``dr``, ``dv``, velocity ``v``,
+    acceleration ``a`` (3-vector Measurements) plus arbitrary keyword attributes (e.g. ``E``)."""
+
+    def __init__(self, **kwargs):
+        self.r = Measurement([0] * 3, "m**1")
+        self.dr = Measurement([0] * 3, "m**1")
+        self.dv = Measurement([0] * 3, "m**1 s**-2")
+        self.v = Measurement([0] * 3, "m**1 s**-1")
+        self.a = Measurement([0] * 3, "m**1 s**-2")
+        for attr, val in kwargs.items():
+            setattr(self, attr, val)
+
+
+class _ObjectList(list):
+    """``sim.objects``: a list that knows when the device store is the authority.
+
+    Mutations mark the host side dirty (the store is rebuilt before the next device step);
+    ``len()`` answers from the device's live count when device steps have retired photons, so the
+    reference's default exit predicate ``len(x.objects) == 0`` (physicl/__init__.py:414) works
+    without copying particles back."""
+
+    def __init__(self, sim):
+        super().__init__()
+        self._sim = sim
+
+    def _touch(self):
+        self._sim._host_dirty = True
+
+    def append(self, o):
+        self._touch()
+        super().append(o)
+
+    def extend(self, it):
+        self._touch()
+        super().extend(it)
+
+    def remove(self, o):
+        self._sim._pull_objects()
+        self._touch()
+        super().remove(o)
+
+    def insert(self, i, o):
+        self._touch()
+        super().insert(i, o)
+
+    def pop(self, *a):
+        self._sim._pull_objects()
+        self._touch()
+        return super().pop(*a)
+
+    def clear(self):
+        self._touch()
+        super().clear()
+
+    def __len__(self):
+        sim = self._sim
+        if sim._device_dirty and sim.store is not None:
+            return sim._device_live_count()
+        return super().__len__()
+
+    def __iter__(self):
+        self._sim._pull_objects()
+        return super().__iter__()
+
+    def __getitem__(self, i):
+        self._sim._pull_objects()
+        return super().__getitem__(i)
+
+
+class Simulation(threading.Thread):
+    """physicl/__init__.py:400-541.  A thread that repeatedly runs its steps, in insertion order,
+    until ``exit(sim)`` is true, then calls every step's ``terminate``.
+
+    Keyword arguments become attributes exactly as in the reference (``bounds``, ``cl_on``, ``exit``,
+    ``state_fn``, ``state_need_lock``).  Added, all optional: ``device`` (CUDA ordinal; default
+    ``$PHYSICL_B200_DEVICE`` or ``$LOCAL_RANK`` or 0), ``seed`` (Philox key for in-kernel draws),
+    ``fuse`` (merge kinematics+scatter+escape+tallies into one kernel per timestep, default True),
+    ``shard`` (under ``torch.distributed``: this rank owns a contiguous slice of the particles)."""
+
+    def __init__(self, **kwargs):
+        threading.Thread.__init__(self)
+        self.bounds = np.zeros(3)
+        self.cl_on = True
+        self.exit = lambda x: len(x.objects) == 0
+        self.state_fn = lambda x: {"objects": len(x.objects), "t": x.t, "dt": x.dt, "run_time": time.time() - x.start_time}
+        self.state_need_lock = False
+        self.device = None
+        self.seed = 0
+        self.fuse = True
+        self.shard = False
+        self.compact_every = 16  # timesteps between live-count checks of the fused photon step
+        for attr, val in kwargs.items():
+            setattr(self, attr, val)
+        self.dt = Measurement(np.double(0), "s**1")
+        self.t = Measurement(np.double(0), "s**1")
+        self.ts = []
+        self.store = None
+        self._host_dirty = True
+        self._device_dirty = False
+        self._pending = None  # bulk particles registered with add_particles()
+        self.objects = _ObjectList(self)
+        self.steps = {}
+        self._state_lock = threading.Lock()
+        self.running = False
+        self.start_time = 0
+        self.step_index = 0
+        self.error = None
+        if self.cl_on:
+            from . import _capi
+
+            if self.device is None:
+                self.device = int(os.environ.get("PHYSICL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            # stands in for cl.create_some_context() + cl.CommandQueue() (physicl/__init__.py:428-429)
+            self.cl_ctx = _capi.Context(self.device)
+            self.cl_q = self.cl_ctx
+        else:
+            self.cl_ctx = None
+            self.cl_q = None
+
+    # ---- registration (physicl/__init__.py:434-468) -------------------------------------------
+    def add_step(self, idx, step):
+        if idx in self.steps:
+            raise IndexException("Cannot add a step to an existing index.")
+        self.steps[idx] = step
+
+    def add_obj(self, obj):
+        self.objects.append(obj)
+
+    def add_objs(self, objs):
+        self.objects.extend(objs)
+
+    def remove_obj(self, obj):
+        self.objects.remove(obj)
+
+    def remove_step(self, idx):
+        if self.running:
+            raise RuntimeError("Cannot remove a Step while the simulation is running.")
+        self.steps.pop(idx)
+
+    def add_particles(self, r, v, E=None, a=None, kind="photon", track_nscat=False, id_base=None):
+        """Bulk ingest for particle counts where one Python object per particle is not an option
+        (hard part 7).  ``r``, ``v``, ``a``: ``(3, N)`` arrays in code units;
+        ``E``: ``(N,)``.  Additive to ``add_obj``; particles added this way have no Python objects
+        until something asks for them.  ``id_base``: global id of the first particle when the caller
+        has already cut its own shard (the Philox counter is the global id)."""
+        if self._pending is None:
+            self._pending = {}
+        if kind in self._pending:
+            raise ValueError("add_particles: one call per kind")
+        self._pending[kind] = dict(r=r, v=v, E=E, a=a, track_nscat=track_nscat, id_base=id_base)
+        self._host_dirty = True
+
+    # ---- device store bridge ------------------------------------------------------------------
+    def _shard_slice(self, n):
+        if not self.shard:
+            return 0, n
+        from .dist import shard_range
+
+        return shard_range(n)
+
+    def device_store(self):
+        """The HBM-resident store, (re)built from ``sim.objects`` / ``add_particles`` when the host
+        side changed since the last device step."""
+        if not self.cl_on:
+            raise RuntimeError("physicl_b200 has no CPU path: device steps need Simulation(cl_on=True)")
+        if self.store is not None and not self._host_dirty:
+            return self.store
+        from .store import DeviceParticleStore
+        from . import light
+
+        self._pull_objects()
+        store = DeviceParticleStore(self.cl_ctx)
+        objs = list.__iter__(self.objects)
+        photons, others = [], []
+        for o in objs:
+            (photons if type(o) is light.PhotonObject else others).append(o)
+        for kind, group in (("photon", photons), ("object", others)):
+            if group:
+                lo, hi = self._shard_slice(len(group))
+                mine = group[lo:hi]
+                r = np.array([np.asarray(o.r, np.float64) for o in mine]).reshape(-1, 3).T
+                v = np.array([np.asarray(o.v, np.float64) for o in mine]).reshape(-1, 3).T
+                E = None
+                if kind == "photon":
+                    E = np.array([np.nan if getattr(o, "E", None) is None else float(np.asarray(o.E)) for o in mine])
+                a = np.array([np.asarray(o.a, np.float64) for o in mine]).reshape(-1, 3).T
+                store.add_group(kind, r, v, E=E, a=a if np.any(a) else None, id_base=lo, host_objs=mine)
+        for kind, p in (self._pending or {}).items():
+            r = np.asarray(p["r"]).reshape(3, -1)
+            lo, hi = self._shard_slice(r.shape[1]) if p["id_base"] is None else (0, r.shape[1])
+            sl = slice(lo, hi)
+            lo = lo if p["id_base"] is None else int(p["id_base"])
+            store.add_group(kind, r[:, sl], np.asarray(p["v"]).reshape(3, -1)[:, sl],
+                            E=None if p["E"] is None else np.asarray(p["E"])[sl],
+                            a=None if p["a"] is None else np.asarray(p["a"]).reshape(3, -1)[:, sl],
+                            id_base=lo, track_nscat=p["track_nscat"])
+        self.store = store
+        self._host_dirty = False
+        self._device_dirty = False
+        self._live_row = None
+        return store
+
+    def _mark_device_dirty(self, live_row=None):
+        self._device_dirty = True
+        if live_row is not None:
+            self._live_row = live_row
+
+    def _device_live_count(self):
+        """Live particles according to the device (all ranks when sharded)."""
+        st = self.store
+        n = 0
+        for kind, g in st.groups.items():
+            if kind == "photon" and getattr(self, "_live_row", None) is not None:
+                n_live = int(st.peek_row(self._live_row)[0])
+                st.maybe_compact("photon", n_live)
+                n += n_live
+            else:
+                n += g.n_live
+        if self.shard:
+            from .dist import all_reduce_int
+
+            n = all_reduce_int(n)
+        return n
+
+    def _pull_objects(self):
+        """Make the Python objects current again (bulk D2H, then per-object attribute writes).
+        Host steps and user code that walk ``sim.objects`` get here; the hot path never does."""
+        if not self._device_dirty or self.store is None:
+            return
+        self._device_dirty = False
+        st = self.store
+        keep = []
+        for kind, g in st.groups.items():
+            snap = st.snapshot(kind, live_only=True)
+            if g.host_objs is None:
+                from . import light
+
+                cls = light.PhotonObject if kind == "photon" else Object
+                g.host_objs = {}
+                for i in snap["id"]:
+                    o = cls.__new__(cls)
+                    Object.__init__(o)
+                    g.host_objs[int(i)] = o
+            for j, i in enumerate(snap["id"]):
+                o = g.host_objs[int(i)]
+                o.r = Measurement([snap["x"][j], snap["y"][j], snap["z"][j]], "")
+                o.r.scale, o.r.units, o.r.original_units = np.double(1), {"L": 1}, {"m": 1}
+                o.v = Measurement([snap["vx"][j], snap["vy"][j], snap["vz"][j]], "")
+                o.v.scale, o.v.units, o.v.original_units = np.double(1), {"L": 1, "T": -1}, {"m": 1, "s": -1}
+                if "dx" in snap:
+                    o.dr = Measurement([snap["dx"][j], snap["dy"][j], snap["dz"][j]], "")
+                    o.dr.scale, o.dr.units, o.dr.original_units = np.double(1), {"L": 1}, {"m": 1}
+                if "E" in snap and kind == "photon":
+                    o.E = np.double(snap["E"][j])
+                if "nscat" in snap:
+                    o.nscat = int(snap["nscat"][j])
+                keep.append(o)
+        list.clear(self.objects)
+        list.extend(self.objects, keep)
+
+    # ---- main loop (physicl/__init__.py:501-524) ----------------------------------------------
+    def _plan(self):
+        """Execution plan for one timestep: the steps in insertion order, with a maximal
+        kinematics -> scatter [-> escape] [-> tallies...] run replaced by one fused launch."""
+        steps = list(self.steps.values())
+        for ordinal, s in enumerate(steps):  # distinct Philox keys for distinct stochastic steps
+            if hasattr(s, "_salt"):
+                s._salt = ((ordinal + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        if not (self.fuse and self.cl_on):
+            return steps
+        from .fused import fuse_plan
+
+        return fuse_plan(steps)
+
+    def run(self):
+        self.start_time = time.time()
+        self.t = 0
+        self.dt = 0
+        self.ts = []
+        self.step_index = 0
+        self.running = True
+        try:
+            plan = self._plan()
+            while not self.exit(self):
+                with self._state_lock:
+                    for step in plan:
+                        if not step.uses_device and getattr(step, "touches_objects", True):
+                            self._pull_objects()
+                            self._host_dirty = self._host_dirty or self.store is not None
+                        step.run(self)
+                    self.step_index += 1
+            with self._state_lock:
+                for step in self.steps.values():
+                    step.terminate(self)
+        except BaseException as e:  # re-raised by join(): a dead thread must not look like success
+            self.error = e
+        finally:
+            self.run_time = time.time() - self.start_time
+            self.running = False
+
+    def join(self, timeout=None):
+        super().join(timeout)
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
+
+    def run_steps(self, nsteps):
+        """Run exactly ``nsteps`` timesteps on the calling thread (no exit predicate, no thread):
+        the bulk entry point used by bench.py."""
+        plan = self._plan()
+        if not self.ts:
+            self.t, self.dt = 0, 0
+        for _ in range(int(nsteps)):
+            for step in plan:
+                if not step.uses_device and getattr(step, "touches_objects", True):
+                    self._pull_objects()
+                    self._host_dirty = self._host_dirty or self.store is not None
+                step.run(self)
+            self.step_index += 1
+
+    # ---- introspection --------------------------------------------------------------------------
+    @staticmethod
+    def get_device_info():
+        """physicl/__init__.py:470-499: {platform: {property..., device: {property...}}}."""
+        from . import _capi
+        import torch
+
+        out = {"NAME": "physicl_b200 (CUDA, sm_100a)"}
+        for d in range(torch.cuda.device_count()):
+            ctx = _capi.Context(d)
+            info = ctx.device_info()
+            out[info["NAME"] + " #%d" % d] = info
+            ctx.close()
+        return {"physicl_b200": out}
+
+    @staticmethod
+    def set_dev(id):
+        """physicl/__init__.py:526-529 (a stub there): choose the default device ordinal."""
+        os.environ["PHYSICL_B200_DEVICE"] = str(id)
+
+    def get_state(self):
+        if self.state_need_lock:
+            with self._state_lock:
+                return self.state_fn(self)
+        return self.state_fn(self)

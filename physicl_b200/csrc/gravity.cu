@@ -121,7 +121,7 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
 // kick-drift (semi-implicit Euler, same ordering as the kinematics law: v first, then r)
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_kick_drift(uint64_t n, float4 *posm, float *vx, float *vy, float *vz, const float *ax, const float *ay,
-                 const float *az, float dt) {
+                 const float *az, float dt, float *x, float *y, float *z) {
     const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
     for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n; i += stride) {
         float4 b = posm[i];
@@ -133,17 +133,24 @@ pcl_k_kick_drift(uint64_t n, float4 *posm, float *vx, float *vy, float *vz, cons
         vy[i] = v;
         vz[i] = w;
         posm[i] = b;
+        if (x) {  // keep the SoA position planes of the store current
+            x[i] = b.x;
+            y[i] = b.y;
+            z[i] = b.z;
+        }
     }
 }
 
 extern "C" int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx, float *vy,
-                                      float *vz, const float *ax, const float *ay, const float *az, float dt) {
+                                      float *vz, const float *ax, const float *ay, const float *az, float dt,
+                                      float *x, float *y, float *z) {
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, posm && vx && vy && vz && ax && ay && az, "null argument");
     PCL_REQUIRE(ctx, pcl_aligned16(posm), "posm must be 16-byte aligned");
+    PCL_REQUIRE(ctx, (x && y && z) || (!x && !y && !z), "x, y, z planes come as a triple or not at all");
     if (n == 0) return 0;
     unsigned grid = pcl_stream_grid(ctx, n, PCL_BLOCK, 8);
-    pcl_k_kick_drift<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(n, (float4 *)posm, vx, vy, vz, ax, ay, az, dt);
+    pcl_k_kick_drift<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(n, (float4 *)posm, vx, vy, vz, ax, ay, az, dt, x, y, z);
     PCL_LAUNCHED(ctx);
     return 0;
 }

@@ -314,6 +314,31 @@ pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
     if (row) pcl_flush_tally(cnt, row, 0u);
 }
 
+// Stand-alone escape sphere.
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_escape(pcl_soa p, float r2_escape, int64_t *row, uint64_t n) {
+    uint32_t cnt[C_PLANE0];
+#pragma unroll
+    for (int q = 0; q < C_PLANE0; ++q) cnt[q] = 0u;
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n; i += stride) {
+        float xx = p.x[i];
+        if (xx != xx) continue;
+        cnt[C_LIVEIN] += 1u;
+        float yy = p.y[i], zz = p.z[i];
+        float r2 = xx * xx;
+        r2 = fmaf(yy, yy, r2);
+        r2 = fmaf(zz, zz, r2);
+        if (r2 >= r2_escape) {
+            cnt[C_ESC] += 1u;
+            p.x[i] = __int_as_float(0x7fc00000);
+        } else {
+            cnt[C_ALIVE] += 1u;
+        }
+    }
+    if (row) pcl_flush_tally(cnt, row, 0u);
+}
+
 // Stand-alone tallies (ScatterSignMeasureStep / ScatterMeasureStep).
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_tally(pcl_soa p, StepK K, int64_t *row, uint64_t n) {
@@ -490,6 +515,17 @@ extern "C" int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, con
         default: PCL_SC(true, true, true); break;
     }
 #undef PCL_SC
+    PCL_LAUNCHED(ctx);
+    return 0;
+}
+
+extern "C" int pcl_escape(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float r2, int64_t *tally_row) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, p != nullptr && p->x && p->y && p->z, "r planes are required");
+    PCL_REQUIRE(ctx, r2 > 0.f, "escape radius must be positive");
+    if (p->n == 0) return 0;
+    unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
+    pcl_k_escape<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(*p, r2, tally_row, p->n);
     PCL_LAUNCHED(ctx);
     return 0;
 }

@@ -1,0 +1,391 @@
+"""Photon objects, emission, scattering steps and their measure steps.
+
+Mirror of the reference's ``physicl/light.py`` (same names, same arguments).  The three OpenCL
+kernels there (light.py:146-158, :239-249, :303-315) and the Python loops around them become
+sm_100a kernels reached through the C ABI; see ``csrc/photon.cu``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import numpy.linalg as np_lin
+
+import physicl_b200 as physicl
+
+from . import _capi
+
+# SI constants, scaled to code units at import exactly like the reference (light.py:14-16):
+# call Measurement.set_code_scale(...) BEFORE importing this module.
+c = physicl.Measurement(np.double(299792458), "m**1 s**-1")
+h = physicl.Measurement(np.double(6.62607015e-34), "J**1 s**1")
+kB = physicl.Measurement(np.double(1.380649e-23), "J**1 K**-1")
+
+
+class PhotonObject(physicl.Object):
+    """light.py:18-35: needs ``E`` and a velocity whose norm equals ``c`` exactly."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        if np_lin.norm(self.v) != np_lin.norm(c):
+            raise Exception("Not a valid speed.")
+        if "E" not in kwargs:
+            raise Exception("Needs a valid energy.")
+
+
+def E_from_wavelength(wavelength):
+    """light.py:39-43"""
+    return (h * c) / wavelength
+
+
+def wavelength_from_E(E):
+    """light.py:45-49"""
+    return (h * c) / E
+
+
+# ---- emission (light.py:53-128) ------------------------------------------------------------------
+def _plain(x):
+    return x.__unscaled__() if isinstance(x, physicl.Measurement) else x
+
+
+def planck_distribution(E, T):
+    """light.py:53-60: 15/(pi^4 kT) (E/kT)^3 e^(-E/kT), as a ``J**-1`` Measurement."""
+    E_conv, T_conv, kB_conv = _plain(E), _plain(T), kB.__unscaled__()
+    x = E_conv / (kB_conv * T_conv)
+    return physicl.Measurement(15 / (np.pi ** 4 * kB_conv * T_conv) * x ** 3 / np.e ** x, "J**-1")
+
+
+def _planck_primitive(E, T):
+    x = E / (float(kB.__unscaled__()) * T)
+    return -np.exp(-x) * (x ** 3 + 3 * x ** 2 + 6 * x + 6) * (15.0 / np.pi ** 4)
+
+
+def planck_probability(E_min, E_max, T, integrator=None):
+    """light.py:63-64: integral of the density over [E_min, E_max] -> ``(value, abserr)``.
+    Default: the closed form (agrees with the reference's scipy.integrate.quad to 1e-13)."""
+    if integrator is not None:
+        return integrator(lambda x: planck_distribution(x, T), E_min, E_max)
+    E_min, E_max, T = float(_plain(E_min)), float(_plain(E_max)), float(_plain(T))
+    return (float(_planck_primitive(E_max, T) - _planck_primitive(E_min, T)), 0.0)
+
+
+def planck_table(E_min, E_max, T, bins):
+    """The reference's binned law (light.py:82-93): grid ``linspace(E_min, E_max, bins)`` and the
+    cumulative, normalised masses of the ``bins-1`` intervals (float64)."""
+    E_min, E_max, T, bins = float(_plain(E_min)), float(_plain(E_max)), float(_plain(T)), int(_plain(bins))
+    E = np.linspace(E_min, E_max, bins)
+    F = _planck_primitive(E, T)
+    gamma = F[1:] - F[:-1]
+    tot = 0.0
+    for gm in gamma:
+        tot += gm
+    norm = gamma / tot
+    cdf = np.empty_like(norm)
+    acc = 0.0
+    for i, gm in enumerate(norm):
+        acc = gm if i == 0 else acc + gm
+        cdf[i] = acc
+    return E, norm, cdf
+
+
+last_planck_params = None
+last_planck_gamma_norm = None
+last_planck_cdf = None
+
+
+def planck_phot_distribution(E_min, E_max, T, bins=1000):
+    """light.py:73-104, host form: one ``np.random.rand()`` per call, returns the GRID energy ``E[x]``
+    of the first ``x >= 1`` with ``cdf[x-1] <= rand <= cdf[x]``, or ``None`` when there is none."""
+    global last_planck_params, last_planck_gamma_norm, last_planck_cdf
+    params = [_plain(x) for x in (E_min, E_max, T, bins)]
+    E = np.linspace(params[0], params[1], params[3])
+    if last_planck_params != params:
+        _, norm, cdf = planck_table(*params)
+        last_planck_params, last_planck_gamma_norm, last_planck_cdf = params, list(norm), list(cdf)
+    cdf = np.asarray(last_planck_cdf)
+    rand = np.random.rand()
+    x = int(np.searchsorted(cdf, rand, side="left"))
+    if x >= cdf.size:
+        return None
+    if x == 0:
+        if cdf.size > 1 and rand == cdf[0]:
+            x = 1
+        else:
+            return None
+    return physicl.Measurement(E[x], "J**1")
+
+
+def planck_sample_device(ctx, n, E_min, E_max, T, bins=1000, seed=0, id_base=0, device=None, want_bins=False):
+    """Device form of the same sampler for bulk emission: one Philox uniform per photon (stream 1),
+    binary search of the float64 table.  Returns ``(e, E0[, bin])``: ``e`` is a float32 CUDA tensor of
+    ``E / E0`` with ``E0 = E_max``; ``bin`` (int32) is the grid index, -1 where the reference yields None."""
+    import torch
+
+    E, _, cdf = planck_table(E_min, E_max, T, bins)
+    E0 = float(E[-1])
+    dev = torch.device("cuda", ctx.device) if device is None else device
+    cdf_d = torch.from_numpy(cdf).to(dev)
+    e = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    b = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_bins else None
+    step = (E[-1] - E[0]) / (len(E) - 1)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ctx.call("pcl_planck_sample", stream, C.c_uint64(n), C.c_uint64(id_base), C.c_uint64(seed), C.c_void_p(cdf_d.data_ptr()),
+             C.c_uint32(cdf.size), C.c_float(E[0] / E0), C.c_float(step / E0), C.c_void_p(e.data_ptr()),
+             C.c_void_p(b.data_ptr()) if b is not None else None)
+    torch.cuda.current_stream(dev).synchronize()  # cdf_d may be freed after return
+    return (e[:n], E0, b[:n]) if want_bins else (e[:n], E0)
+
+
+def generate_photons_from_E(E):
+    """light.py:109-110"""
+    return [PhotonObject(E=x, v=c * [1, 0, 0]) for x in E]
+
+
+def generate_photons(n, fn=lambda: np.random.power(3), min=0, max=0, bins=-1):
+    """light.py:112-128: ``E = min + (max - min) * fn()``, photons start at the origin along +x."""
+    out = []
+    for _ in range(int(n)):
+        Eo = min + (max - min) * fn()
+        out.append(PhotonObject(E=Eo, v=physicl.Measurement([c, 0, 0], "m**1 s**-1")))
+    return out
+
+
+# ---- scattering steps ------------------------------------------------------------------------------
+class _ScatterBase(physicl.Step):
+    uses_device = True
+    mode = 0
+
+    def _init_rng(self, rng, seed):
+        if rng not in ("philox", "numpy"):
+            raise ValueError("rng must be 'philox' (in-kernel) or 'numpy' (the reference's host draws)")
+        self.rng = rng
+        self.seed = seed
+        self._salt = 0  # set from the step's position in the simulation (Simulation._plan)
+
+    def _seed(self, sim):
+        return (int(self.seed) if self.seed is not None else (int(sim.seed) ^ self._salt)) & 0xFFFFFFFFFFFFFFFF
+
+    def scatter_params(self, group):
+        k = float(self.A) * float(self.n)
+        mode = self.mode
+        if getattr(self, "wavelength_dep_scattering", False):
+            # pcoll = A n |dr| (h c / E)^-4 (light.py:300-301) = [A n (E0 / (h c))^4] |dr| (E/E0)^4
+            k = k * (group.e0 / (float(h) * float(c))) ** 4
+            mode |= _capi.SCATTER_WAVELENGTH
+        return _capi.ScatterParams(k=k, c=float(c), mode=mode)
+
+    def rng_params(self, sim, store, group):
+        """Philox: nothing to upload.  'numpy': draw on the host in the reference's order
+        (light.py:285: rtheta, rphi, rand per photon; light.py:235: rand only) and inject."""
+        r = _capi.Rng(seed=self._seed(sim), step=sim.step_index & 0xFFFFFFFF)
+        keep = None
+        if self.rng == "numpy":
+            import torch
+
+            if group.n_live != group.n:
+                store.compact("photon")  # one draw per LIVE photon, in list order (light.py:235)
+            n = group.n
+            if self.mode & _capi.SCATTER_DELETE:
+                u = np.random.random(n).astype(np.float32)
+                keep = (torch.from_numpy(u).to(store.device),)
+                r.u_rand = keep[0].data_ptr()
+            else:
+                u = np.random.random((n, 3)).astype(np.float32)
+                keep = tuple(torch.from_numpy(np.ascontiguousarray(u[:, i])).to(store.device) for i in range(3))
+                r.u_theta, r.u_phi, r.u_rand = (t.data_ptr() for t in keep)
+        return r, keep
+
+    def run(self, sim):
+        """Unfused form: reads the dr planes the kinematics step wrote (as the reference kernel does)."""
+        st = sim.device_store()
+        g = st.group("photon")
+        if g is None or g.n == 0:
+            return
+        if "dx" not in g.planes:
+            raise RuntimeError("%s needs the displacement of this timestep: add NewtonianKinematicsStep before it "
+                               "(reference pipelines do: test/test_light.py:33-34)" % type(self).__name__)
+        sp = self.scatter_params(g)
+        rng, keep = self.rng_params(sim, st, g)
+        row = st.new_row()
+        soa = g.soa()
+        sim.cl_ctx.call("pcl_scatter", st.stream(), C.byref(soa), C.byref(sp), C.byref(rng), None, st.row_ptr())
+        if keep is not None:
+            st.synchronize()
+        sim._mark_device_dirty(live_row=row)
+        if self.mode & _capi.SCATTER_DELETE and self.rng == "numpy":
+            g.n_live = int(st.peek_row(row)[_capi.T_ALIVE])
+
+
+class ScatterIsotropicStep(_ScatterBase):
+    """light.py:262-359.  ``n`` number density, ``A`` cross-section; ``wavelength_dep_scattering``
+    multiplies the collision probability by ``(h c / E)^-4``.  New keyword arguments: ``rng``
+    ('philox' in-kernel draws, or 'numpy' for the reference's host-side ``np.random`` stream) and ``seed``.
+
+    Note the direction law is the reference's: theta ~ U[0, 2 pi) polar, phi ~ U[0, pi) azimuth
+    (light.py:285, :309-311), which is not uniform on the sphere."""
+
+    def __init__(self, **kwargs):
+        self.n = kwargs.get("n", 1)
+        self.A = kwargs.get("A", 1)
+        self.wavelength_dep_scattering = kwargs.get("wavelength_dep_scattering", False)
+        self.variable_n = kwargs.get("variable_n", False)
+        self.variable_n_fn = kwargs.get("variable_n_fn", None)
+        if self.variable_n:
+            raise NotImplementedError("variable_n splices a user OpenCL-C expression into the kernel (light.py:295-299); "
+                                      "it is outside this backend's hand-written kernels (SURVEY.md section 8f)")
+        self._init_rng(kwargs.get("rng", "philox"), kwargs.get("seed", None))
+
+
+class ScatterDeleteStep(_ScatterBase):
+    """light.py:225-260: photons whose collision test succeeds are removed from the simulation."""
+
+    mode = _capi.SCATTER_DELETE
+
+    def __init__(self, n, A, rng="philox", seed=None):
+        self.n, self.A = n, A
+        self._init_rng(rng, seed)
+
+
+class ScatterDeleteStepReference(ScatterDeleteStep):
+    """light.py:131-223: the hand-written twin of ``ScatterDeleteStep``; same law, same kernel here."""
+
+
+class EscapeSphereStep(physicl.Step):
+    """Photons with ``|r| >= R`` leave the simulation (NOT in the reference, whose ``bounds`` is never
+    read).  ``escaped`` collects the per-timestep escape counts: the
+    escape-time histogram."""
+
+    uses_device = True
+
+    def __init__(self, R):
+        self.R = float(R)
+        self._rows = []
+
+    def run(self, sim):
+        st = sim.device_store()
+        g = st.group("photon")
+        if g is None or g.n == 0:
+            return
+        row = st.new_row()
+        soa = g.soa()
+        sim.cl_ctx.call("pcl_escape", st.stream(), C.byref(soa), C.c_float(self.R * self.R), st.row_ptr())
+        self._rows.append((sim.store, row))
+        sim._mark_device_dirty(live_row=row)
+
+    def _note_row(self, sim, row):
+        self._rows.append((sim.store, row))
+
+    @property
+    def escaped(self):
+        return np.array([int(st.read_row(r)[_capi.T_ESCAPED]) for st, r in self._rows], np.int64)
+
+    def escaped_all_ranks(self):
+        from .dist import all_reduce_rows
+
+        return all_reduce_rows(self.escaped)
+
+
+# ---- measure steps -------------------------------------------------------------------------------
+class _DeviceMeasureStep(physicl.MeasureStep):
+    """Rows are tallied on the device and fetched lazily: reading ``data`` costs one D2H copy for all
+    pending rows instead of one blocking read per timestep."""
+
+    uses_device = True
+
+    def __init__(self, out_fn):
+        super().__init__(out_fn)
+        self._data = []
+        self._pending = []  # (t, store, global row)
+
+    @property
+    def data(self):
+        if self._pending:
+            pend, self._pending = self._pending, []
+            rows = np.stack([st.read_row(row) for _, st, row, _ in pend])
+            if pend[0][3]:  # sharded: every rank holds partial counts; sum them once for all rows
+                from .dist import all_reduce_rows
+
+                rows = all_reduce_rows(rows)
+            for (t, _, _, _), r in zip(pend, rows):
+                self._data.append(self._format(t, r))
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data = v
+        self._pending = []
+
+    def _note_row(self, sim, row):
+        if hasattr(row, "plane_slice") and hasattr(self, "_plane0"):
+            self._plane0 = row.plane_slice[0]
+        self._pending.append((sim.t, sim.store, int(row), bool(sim.shard)))
+
+    def _planes(self):
+        return []
+
+    def run(self, sim):
+        st = sim.device_store()
+        row = st.new_row()
+        pl = _capi.make_planes(self._planes())
+        for g in st.groups.values():
+            if g.n == 0:
+                continue
+            if pl.count:
+                g.ensure("dx", "dy", "dz")
+            soa = g.soa()
+            sim.cl_ctx.call("pcl_tally", st.stream(), C.byref(soa), C.byref(pl), st.row_ptr())
+        self._note_row(sim, row)
+
+
+class ScatterMeasureStep(_DeviceMeasureStep):
+    """light.py:361-404: row ``[t, N, crossings of each plane...]``; a plane is a 3-vector with NaN in
+    the two free coordinates; a crossing is ``r - dr <= loc <= r`` or ``r - dr >= loc >= r``."""
+
+    def __init__(self, out_fn, measure_n=True, measure_locs=[], measure_E=False):
+        super().__init__(out_fn)
+        self.measure_locs = measure_locs
+        self.measure_n = measure_n
+        self.measure_E = measure_E
+        self._plane0 = 0  # first tally column of this step's planes (non-zero only inside a fused row)
+        if measure_E:
+            raise NotImplementedError("measure_E (energy lists of plane crossers, light.py:388-402) is not on the "
+                                      "device path yet (SURVEY.md section 8f rank 1)")
+
+    def _planes(self):
+        out = []
+        for loc in self.measure_locs:
+            loc = np.asarray(loc, np.float64)
+            ax = 0 if not np.isnan(loc[0]) else (1 if not np.isnan(loc[1]) else 2)  # light.py:385-395
+            out.append((ax, float(loc[ax])))
+        return out
+
+    def _format(self, t, r):
+        out = [t]
+        if self.measure_n:
+            out.append(int(r[_capi.T_ALIVE]))
+        out.extend(int(r[_capi.T_PLANE0 + self._plane0 + k]) for k in range(len(self.measure_locs)))
+        return np.array(out)
+
+
+class ScatterSignMeasureStep(_DeviceMeasureStep):
+    """light.py:406-431: row ``[t, N, #(v_x > 0), #(v_y > 0), #(v_z > 0)]`` over all objects."""
+
+    def __init__(self, out_fn, measure_n=True):
+        super().__init__(out_fn)
+        self.measure_n = measure_n
+
+    def _format(self, t, r):
+        out = [t]
+        if self.measure_n:
+            out.append(int(r[_capi.T_ALIVE]))
+        out.extend(int(r[q]) for q in (_capi.T_XP, _capi.T_YP, _capi.T_ZP))
+        return np.array(out)
+
+
+class TracePathMeasureStep(physicl.MeasureStep):
+    """light.py:433-483 keeps a deep copy of every object's position every timestep: an O(N * steps)
+    host trace, out of scope for the device path.  Use
+    ``sim.store.snapshot()`` at the cadence you need, or ``track_nscat`` for scatter counts."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(self.__doc__)

@@ -1,0 +1,232 @@
+"""Device-resident particle state: structure-of-arrays float32 planes in HBM.
+
+The reference keeps particles as a Python list of ``Object`` instances whose fields are 3-vector
+``Measurement`` arrays (physicl/__init__.py:381-396) and re-marshals them to the device on every
+step (``CLProgram.run``, :602-664).  Here the state is uploaded once and stays on the GPU; PyTorch
+is used only to own the buffers (``torch.empty(..., device="cuda")``) and every kernel launch goes
+through the C ABI with raw pointers.
+
+A store holds up to two homogeneous groups, because the reference's scatter steps act on
+``PhotonObject`` only (light.py:283) while kinematics and the sign tally act on every object
+(newton.py:14, light.py:423): ``photon`` and ``object``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+_PLANES_F32 = ("x", "y", "z", "vx", "vy", "vz", "dx", "dy", "dz", "ax", "ay", "az", "e")
+_PLANES_U32 = ("id", "nscat")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class Group:
+    """One SoA block.  ``n`` counts slots (live + retired); a retired slot has x = NaN."""
+
+    def __init__(self, kind, device, n, id_base=0):
+        self.kind, self.device, self.n, self.id_base = kind, device, int(n), int(id_base)
+        self.planes = {}
+        self.spare = {}  # ping-pong partners used by compaction
+        self.e0 = 1.0  # energy scale: the e plane holds E / e0
+        self.host_objs = None  # python objects by local id, when the group came from sim.objects
+        self.n_live = int(n)  # last known live count (exact after sync_live)
+
+    def alloc(self, name, fill=None):
+        torch = _torch()
+        dt = torch.int32 if name in _PLANES_U32 else torch.float32
+        t = torch.empty(max(self.n, 1), dtype=dt, device=self.device)
+        if fill is not None:
+            t.fill_(fill)
+        self.planes[name] = t
+        return t
+
+    def ensure(self, *names, fill=0):
+        for nm in names:
+            if nm not in self.planes:
+                self.alloc(nm, fill)
+
+    def upload(self, name, host):
+        torch = _torch()
+        if name in _PLANES_U32:
+            arr = np.ascontiguousarray(host, np.uint32).view(np.int32)
+        else:
+            arr = np.ascontiguousarray(host, np.float32)
+        assert arr.size == self.n, (name, arr.size, self.n)
+        t = torch.from_numpy(arr.copy() if arr.size else np.zeros(1, arr.dtype))
+        self.planes[name] = t.to(self.device, non_blocking=False)
+
+    def download(self, name):
+        a = self.planes[name][: self.n].cpu().numpy()
+        return a.view(np.uint32) if name in _PLANES_U32 else a
+
+    def soa(self, planes=None, offset=0, count=None):
+        """Fill a ``pcl_soa`` with raw device pointers (optionally a sub-range of slots)."""
+        s = _capi.Soa()
+        src = self.planes if planes is None else planes
+        cnt = self.n - offset if count is None else count
+        s.n = cnt
+        for nm in _PLANES_F32 + _PLANES_U32:
+            t = src.get(nm)
+            setattr(s, nm, (t.data_ptr() + 4 * offset) if t is not None else None)
+        s.id_base = self.id_base + (offset if src.get("id") is None else 0)
+        return s
+
+    def state_bytes_per_slot(self):
+        return 4 * len(self.planes)
+
+
+class DeviceParticleStore:
+    """All particles of one ``Simulation`` on one GPU, plus the device tally table."""
+
+    TALLY_ROWS = 4096
+
+    def __init__(self, ctx: _capi.Context, compact_threshold=0.125):
+        torch = _torch()
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+        self.groups = {}
+        self.compact_threshold = compact_threshold
+        self.tally = torch.zeros((self.TALLY_ROWS, _capi.TALLY_COLS), dtype=torch.int64, device=self.device)
+        self._row = -1  # row currently being accumulated
+        self._rows_host = {}  # flushed rows: global row number -> np.int64[16]
+        self._row_base = 0  # global row number of tally[0]
+        self._live_scratch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.compactions = 0
+
+    # ---- streams ----------------------------------------------------------------------------
+    def stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    # ---- construction -----------------------------------------------------------------------
+    def add_group(self, kind, r, v, E=None, a=None, id_base=0, host_objs=None, track_nscat=False):
+        """r, v, a: (3, N) array-likes in code units; E: (N,) or None."""
+        r = np.asarray(r, np.float64).reshape(3, -1)
+        v = np.asarray(v, np.float64).reshape(3, -1)
+        n = r.shape[1]
+        if kind in self.groups:
+            raise ValueError("group '%s' already present; build the store once from all particles" % kind)
+        if n >= 2 ** 32:
+            raise ValueError("a shard holds fewer than 2^32 slots")
+        g = Group(kind, self.device, n, id_base)
+        for i, nm in enumerate(("x", "y", "z")):
+            g.upload(nm, r[i])
+        for i, nm in enumerate(("vx", "vy", "vz")):
+            g.upload(nm, v[i])
+        if a is not None:
+            a = np.asarray(a, np.float64).reshape(3, -1)
+            for i, nm in enumerate(("ax", "ay", "az")):
+                g.upload(nm, a[i])
+        if E is not None:
+            E = np.asarray(E, np.float64).reshape(-1)
+            finite = E[np.isfinite(E)]
+            g.e0 = float(np.max(np.abs(finite))) if finite.size and np.max(np.abs(finite)) > 0 else 1.0
+            g.upload("e", E / g.e0)
+        if track_nscat:
+            g.alloc("nscat", 0)
+        g.host_objs = host_objs
+        self.groups[kind] = g
+        return g
+
+    def group(self, kind):
+        return self.groups.get(kind)
+
+    @property
+    def n_slots(self):
+        return sum(g.n for g in self.groups.values())
+
+    # ---- tally rows -------------------------------------------------------------------------
+    def new_row(self):
+        """Start a fresh tally row (one per timestep) and return its global number."""
+        self._row += 1
+        if self._row >= self.TALLY_ROWS:
+            self.flush_rows()
+        return self._row_base + self._row
+
+    def row_ptr(self, global_row=None):
+        local = self._row if global_row is None else global_row - self._row_base
+        assert 0 <= local < self.TALLY_ROWS
+        return C.c_void_p(self.tally.data_ptr() + local * _capi.TALLY_COLS * 8)
+
+    @property
+    def current_row(self):
+        return self._row_base + self._row
+
+    def flush_rows(self):
+        """Bring every accumulated row to the host (one D2H copy) and recycle the table."""
+        if self._row >= 0:
+            host = self.tally[: self._row + 1].cpu().numpy()
+            for i in range(host.shape[0]):
+                self._rows_host[self._row_base + i] = host[i].copy()
+            self.tally[: self._row + 1].zero_()
+            self._row_base += self._row + 1
+            self._row = -1
+
+    def read_row(self, global_row):
+        if global_row not in self._rows_host:
+            self.flush_rows()
+        return self._rows_host[global_row]
+
+    def peek_row(self, global_row):
+        """Read one row without recycling the table (a small blocking D2H)."""
+        if global_row in self._rows_host:
+            return self._rows_host[global_row]
+        return self.tally[global_row - self._row_base].cpu().numpy()
+
+    # ---- compaction -------------------------------------------------------------------------
+    def compact(self, kind="photon"):
+        """Drop retired slots (stable).  Returns the live count."""
+        g = self.groups[kind]
+        if g.n == 0:
+            return 0
+        for nm, t in g.planes.items():
+            if nm not in g.spare or g.spare[nm].numel() < t.numel():
+                g.spare[nm] = _torch().empty_like(t)
+        if "id" not in g.spare:
+            g.spare["id"] = _torch().empty(max(g.n, 1), dtype=_torch().int32, device=self.device)
+        src = g.soa()
+        dst = g.soa(planes=g.spare)
+        self.ctx.call("pcl_compact", self.stream(), C.byref(src), C.byref(dst), C.c_void_p(self._live_scratch.data_ptr()))
+        n_live = int(self._live_scratch.item())
+        had_id = "id" in g.planes
+        g.planes, g.spare = g.spare, g.planes
+        if not had_id:
+            g.spare.pop("id", None)
+        g.n = n_live
+        g.n_live = n_live
+        self.compactions += 1
+        return n_live
+
+    def maybe_compact(self, kind, n_live):
+        g = self.groups.get(kind)
+        if g is None:
+            return False
+        g.n_live = int(n_live)
+        if g.n and (g.n - n_live) > self.compact_threshold * g.n:
+            self.compact(kind)
+            return True
+        return False
+
+    # ---- host views -------------------------------------------------------------------------
+    def snapshot(self, kind="photon", live_only=True):
+        """Download one group as float32/uint32 numpy planes (plus ``id``)."""
+        g = self.groups[kind]
+        out = {nm: g.download(nm) for nm in g.planes}
+        if "id" not in out:
+            out["id"] = np.arange(g.n, dtype=np.uint32)
+        if live_only:
+            keep = ~np.isnan(out["x"])
+            out = {k: v[keep] for k, v in out.items()}
+        if "e" in out:
+            out["E"] = out["e"].astype(np.float64) * g.e0
+        return out

@@ -1,0 +1,480 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's
+golden vectors.  Bar: integer / decision / tally work bit-exact; float state bit-exact against the
+binary32 twin and within 1e-5 (relative to |v| = c, resp. the path length) of the float64 reference.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import reference_law as law
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from physicl_b200 import _capi
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    c = _capi.Context(0)
+    yield c
+    c.close()
+
+
+def _u():
+    import gpu_util
+
+    return gpu_util
+
+
+# ---------------------------------------------------------------------------------------------
+# kinematics (newton.py:14-16)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 1023, 4096 + 5, 1_000_003])
+@pytest.mark.parametrize("accel", [0, 1, 2])
+def test_kinematics_bit_exact_vs_twin(ctx, n, accel):
+    u = _u()
+    rng = np.random.default_rng(n + accel)
+    r = rng.uniform(-1e3, 1e3, (3, n))
+    v = rng.normal(0, 10, (3, n))
+    a = rng.normal(0, 9.81, (3, n)) if accel == 1 else None
+    st, g = u.make_store(ctx, r, v, a=a, kind="object")
+    g.ensure("dx", "dy", "dz")
+    host = u.host_state(g)
+    au = np.array([0.0, 0.0, -9.81], np.float32)
+    for s, dt in enumerate([1e-3, 2.5e-3, 0.5]):
+        soa = g.soa()
+        ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(dt), int(accel != 0),
+                 au.ctypes.data_as(C.POINTER(C.c_float)) if accel == 2 else None)
+        oracle.kinematics_f32(host, dt, accel, au if accel == 2 else None)
+    for nm in host:
+        assert u.same_bits(g.download(nm), host[nm]), nm
+
+
+def test_kinematics_unaligned_view_takes_scalar_path(ctx):
+    u = _u()
+    n = 10_001
+    rng = np.random.default_rng(1)
+    st, g = u.make_store(ctx, rng.uniform(-1e3, 1e3, (3, n)), rng.normal(0, 10, (3, n)), kind="object")
+    g.ensure("dx", "dy", "dz")
+    host = {k: v[1:].copy() for k, v in u.host_state(g).items()}
+    soa = g.soa(offset=1)  # every plane pointer is now 4 bytes past a 16-byte boundary
+    ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(1e-3), 0, None)
+    oracle.kinematics_f32(host, 1e-3)
+    for nm in host:
+        assert u.same_bits(g.download(nm)[1:], host[nm]), nm
+
+
+def test_kinematics_graph_steps_equal_single_steps(ctx):
+    u = _u()
+    n = 200_003
+    rng = np.random.default_rng(5)
+    r, v = rng.uniform(-1e3, 1e3, (3, n)), rng.normal(0, 10, (3, n))
+    st1, g1 = u.make_store(ctx, r, v, kind="object")
+    st2, g2 = u.make_store(ctx, r, v, kind="object")
+    au = np.array([0.0, 0.0, -9.81], np.float32)
+    pau = au.ctypes.data_as(C.POINTER(C.c_float))
+    for _ in range(2):  # second call replays the cached graph
+        s1 = g1.soa()
+        ctx.call("pcl_kinematics_steps", st1.stream(), C.byref(s1), C.c_float(1e-3), 1, pau, C.c_uint32(25))
+    for _ in range(50):
+        s2 = g2.soa()
+        ctx.call("pcl_kinematics", st2.stream(), C.byref(s2), C.c_float(1e-3), 1, pau)
+    for nm in ("x", "y", "z", "vx", "vy", "vz"):
+        assert u.same_bits(g1.download(nm), g2.download(nm)), nm
+
+
+def test_kinematics_matches_reference_golden(ctx, golden):
+    u = _u()
+    gd = golden("kin")
+    st, g = u.make_store(ctx, gd["r0"], gd["v0"], kind="object")
+    g.ensure("dx", "dy", "dz")
+    for s in range(int(gd["nsteps"])):
+        soa = g.soa()
+        ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(float(gd["dts"][s])), 0, None)
+        r = np.stack([g.download(nm) for nm in ("x", "y", "z")]).astype(np.float64)
+        dr = np.stack([g.download(nm) for nm in ("dx", "dy", "dz")]).astype(np.float64)
+        # tolerance: 1e-5 relative per step (north star); float32 gives ~1e-7
+        np.testing.assert_allclose(r, gd["s%d_r" % s], rtol=1e-5, atol=1e-5 * np.abs(gd["r0"]).max())
+        np.testing.assert_allclose(dr, gd["s%d_dr" % s], rtol=1e-5, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused photon step against the binary32 twin (Philox in-kernel)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, oracle.WAVELENGTH, oracle.DELETE, oracle.WAVELENGTH | oracle.DELETE])
+@pytest.mark.parametrize("n", [1, 5, 4096, 250_007])
+def test_fused_step_bit_exact_vs_twin(ctx, mode, n):
+    u = _u()
+    r, v = u.random_photons(n, seed=n + mode)
+    rng = np.random.default_rng(99)
+    E = rng.uniform(0.2, 1.0, n) * 4e-19 if mode & oracle.WAVELENGTH else None
+    st, g = u.make_store(ctx, r, v, E=E, id_base=10_000_000_000, nscat=True)
+    host = u.host_state(g)
+    dt, k, c = 1e-3, 1.2e-6, u.C_LIGHT
+    planes = [(0, 1.0e5), (1, -2.0e5), (2, 0.0)]
+    r2 = 5.0e5 ** 2
+    for step in range(6):
+        got = u.photon_step(ctx, st, g, dt, k, c, mode, seed=2024, step=step, r2_escape=r2, planes=planes)
+        want = oracle.photon_step_f32(host, dt, k, c, mode, seed=2024, step=step, r2_escape=r2, planes=planes,
+                                      id_base=10_000_000_000)
+        assert np.array_equal(got, want), (step, got, want)
+    for nm in host:
+        assert u.same_bits(g.download(nm), host[nm]), nm
+    if n >= 4096:
+        assert want[oracle.T_ALIVE] < n  # something retired, something scattered
+        assert host["nscat"].sum() > 0 or mode & oracle.DELETE
+
+
+def test_fused_equals_unfused_sequence(ctx):
+    """kinematics -> scatter -> escape -> tally as four launches gives the fused launch's bits."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 100_003
+    r, v = u.random_photons(n, seed=3)
+    stA, gA = u.make_store(ctx, r, v)
+    stB, gB = u.make_store(ctx, r, v)
+    gB.ensure("dx", "dy", "dz")
+    dt, k, c, r2 = 1e-3, 1.5e-6, u.C_LIGHT, 4.5e5 ** 2
+    planes = [(0, 5e4)]
+    for step in range(5):
+        rowA = u.photon_step(ctx, stA, gA, dt, k, c, 0, seed=7, step=step, r2_escape=r2, planes=planes)
+        sp = _capi.ScatterParams(k=k, c=c, mode=0)
+        rg = _capi.Rng(seed=7, step=step)
+        soa = gB.soa()
+        ctx.call("pcl_kinematics", stB.stream(), C.byref(soa), C.c_float(dt), 0, None)
+        r1 = stB.new_row()
+        ctx.call("pcl_scatter", stB.stream(), C.byref(soa), C.byref(sp), C.byref(rg), None, stB.row_ptr())
+        r2row = stB.new_row()
+        ctx.call("pcl_escape", stB.stream(), C.byref(soa), C.c_float(r2), stB.row_ptr())
+        r3 = stB.new_row()
+        pl = _capi.make_planes(planes)
+        ctx.call("pcl_tally", stB.stream(), C.byref(soa), C.byref(pl), stB.row_ptr())
+        sc, es, ta = stB.read_row(r1), stB.read_row(r2row), stB.read_row(r3)
+        assert sc[_capi.T_SCATTERED] == rowA[_capi.T_SCATTERED]
+        assert es[_capi.T_ESCAPED] == rowA[_capi.T_ESCAPED]
+        for col in (_capi.T_ALIVE, _capi.T_XP, _capi.T_YP, _capi.T_ZP, _capi.T_PLANE0):
+            assert ta[col] == rowA[col], col
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(gA.download(nm), gB.download(nm)), nm
+
+
+def test_scatter_flags_match_twin(ctx):
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 50_001
+    r, v = u.random_photons(n, seed=8)
+    st, g = u.make_store(ctx, r, v)
+    g.ensure("dx", "dy", "dz")
+    soa = g.soa()
+    ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(1e-3), 0, None)
+    host = u.host_state(g)
+    flags_d = torch.empty(n, dtype=torch.int32, device=st.device)
+    sp = _capi.ScatterParams(k=1e-6, c=u.C_LIGHT, mode=_capi.SCATTER_DELETE)
+    rg = _capi.Rng(seed=5, step=3)
+    row = st.new_row()
+    ctx.call("pcl_scatter", st.stream(), C.byref(soa), C.byref(sp), C.byref(rg), C.c_void_p(flags_d.data_ptr()), st.row_ptr())
+    flags, want_row = oracle.scatter_f32(host, 1e-6, u.C_LIGHT, oracle.DELETE, seed=5, step=3)
+    assert np.array_equal(flags_d.cpu().numpy(), flags)
+    assert 0 < flags.sum() < n
+    got = st.read_row(row)
+    for col in (_capi.T_ALIVE, _capi.T_SCATTERED, _capi.T_ABSORBED, _capi.T_LIVE_IN):
+        assert got[col] == want_row[col]
+    assert u.same_bits(g.download("x"), host["x"])
+
+
+# ---------------------------------------------------------------------------------------------
+# against the reference's own outputs (golden vectors, injected uniforms)
+# ---------------------------------------------------------------------------------------------
+def _split_u(uu):
+    uu = uu.reshape(-1, 3)
+    return [np.ascontiguousarray(uu[:, i], np.float32) for i in range(3)]
+
+
+@pytest.mark.parametrize("name", ["iso", "wave"])
+def test_fused_step_tracks_reference_golden(ctx, golden, name):
+    from physicl_b200 import _capi
+
+    u = _u()
+    gd = golden(name)
+    N, c, dt = int(gd["N"]), float(gd["c"]), float(gd["dt"])
+    r, v = u.beam_photons(N, c)
+    E = gd["E"] if name == "wave" else None
+    st, g = u.make_store(ctx, r, v, E=E)
+    k, mode = float(gd["A"]) * float(gd["n"]), 0
+    if name == "wave":
+        k *= (g.e0 / (float(gd["h"]) * c)) ** 4
+        mode = _capi.SCATTER_WAVELENGTH
+    planes = [(0, 4.0e5), (1, 0.0), (2, -1.0e5)] if name == "iso" else None
+    for s in range(int(gd["nsteps"])):
+        row = u.photon_step(ctx, st, g, dt, k, c, mode, uniforms=_split_u(gd["s%d_u" % s]), planes=planes)
+        ref_hit = ~np.isnan(gd["s%d_res0" % s])
+        assert int(row[_capi.T_SCATTERED]) == int(ref_hit.sum())  # decisions identical
+        vv = np.stack([g.download(nm) for nm in ("vx", "vy", "vz")]).astype(np.float64)
+        rr = np.stack([g.download(nm) for nm in ("x", "y", "z")]).astype(np.float64)
+        assert np.abs(vv - gd["s%d_v" % s]).max() <= 1e-5 * c
+        assert np.abs(rr - gd["s%d_r" % s]).max() <= 1e-5 * c * dt * (s + 1)
+        srow = gd["sign_rows"][s]
+        assert [int(row[q]) for q in (_capi.T_ALIVE, _capi.T_XP, _capi.T_YP, _capi.T_ZP)] == [int(q) for q in srow[1:5]]
+        if planes:
+            assert [int(row[_capi.T_PLANE0 + q]) for q in range(3)] == [int(q) for q in gd["plane_rows"][s][2:5]]
+
+
+@pytest.mark.parametrize("name", ["delete", "delete_ref"])
+def test_delete_matches_reference_golden(ctx, golden, name):
+    from physicl_b200 import _capi
+
+    u = _u()
+    gd = golden(name)
+    N, c, dt = int(gd["N"]), float(gd["c"]), float(gd["dt"])
+    r, v = u.beam_photons(N, c)
+    st, g = u.make_store(ctx, r, v)
+    k = float(gd["A"]) * float(gd["n"])
+    alive = np.arange(N)
+    for s in range(int(gd["nsteps"])):
+        ur = np.zeros(N, np.float32)
+        ur[alive] = gd["s%d_u" % s].astype(np.float32)
+        row = u.photon_step(ctx, st, g, dt, k, c, _capi.SCATTER_DELETE, uniforms=(None, None, ur),
+                            planes=[(0, float(gd["planes"][0][0]))])
+        alive = np.nonzero(~np.isnan(g.download("x")))[0]
+        assert np.array_equal(alive, gd["s%d_gid" % s])
+        prow = gd["plane_rows"][s]
+        assert int(row[_capi.T_ALIVE]) == int(prow[1]) and int(row[_capi.T_PLANE0]) == int(prow[2])
+        assert int(row[_capi.T_ABSORBED]) == int((gd["s%d_flags" % s] == 1).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# compaction (Simulation.remove_obj, physicl/__init__.py:455-459)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 1024, 1025, 300_001])
+def test_compaction_is_stable_and_exact(ctx, n):
+    u = _u()
+    r, v = u.random_photons(n, seed=n)
+    E = np.linspace(1.0, 2.0, n)
+    st, g = u.make_store(ctx, r, v, E=E, nscat=True)
+    rng = np.random.default_rng(n)
+    dead = rng.random(n) < 0.4
+    x = g.download("x").copy()
+    x[dead] = np.nan
+    g.upload("x", x)
+    before = u.host_state(g)
+    n_live = st.compact("photon")
+    keep = ~dead
+    assert n_live == int(keep.sum()) == g.n
+    assert np.array_equal(g.download("id"), np.nonzero(keep)[0].astype(np.uint32))
+    for nm in before:
+        assert u.same_bits(g.download(nm), before[nm][keep]), nm
+    # a second compaction with nothing retired is the identity
+    again = u.host_state(g)
+    assert st.compact("photon") == n_live
+    for nm in again:
+        assert u.same_bits(g.download(nm), again[nm]), nm
+
+
+def test_tallies_do_not_depend_on_compaction(ctx):
+    u = _u()
+    n = 120_000
+    r, v = u.beam_photons(n)
+    stA, gA = u.make_store(ctx, r, v)
+    stB, gB = u.make_store(ctx, r, v)
+    dt, k, c, r2 = 1e-3, 1e-6, u.C_LIGHT, 1.0e6 ** 2
+    rowsA, rowsB = [], []
+    for step in range(40):
+        rowsA.append(u.photon_step(ctx, stA, gA, dt, k, c, 0, seed=11, step=step, r2_escape=r2).copy())
+        rowsB.append(u.photon_step(ctx, stB, gB, dt, k, c, 0, seed=11, step=step, r2_escape=r2).copy())
+        if step % 5 == 4:
+            stB.compact("photon")
+    a, b = np.array(rowsA), np.array(rowsB)
+    assert np.array_equal(a, b)
+    assert b[-1, 0] < n and stB.compactions == 8 and gB.n < gA.n
+    # survivors carry identical state (matched by id)
+    sa, sb = stA.snapshot("photon"), stB.snapshot("photon")
+    assert np.array_equal(sa["id"], sb["id"])
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(sa[nm], sb[nm]), nm
+
+
+# ---------------------------------------------------------------------------------------------
+# emission (light.py:73-104)
+# ---------------------------------------------------------------------------------------------
+def test_planck_bins_bit_exact_and_chi_square(ctx, golden):
+    import physicl_b200.light as light
+    from scipy import stats
+
+    gd = golden("planck")
+    n = 400_000
+    e, E0, b = light.planck_sample_device(ctx, n, float(gd["E_min"]), float(gd["E_max"]), float(gd["T"]),
+                                          bins=int(gd["bins"]), seed=2025, id_base=123, want_bins=True)
+    E, norm, cdf = light.planck_table(float(gd["E_min"]), float(gd["E_max"]), float(gd["T"]), int(gd["bins"]))
+    np.testing.assert_allclose(cdf, gd["cdf"], rtol=1e-11)  # same table as the reference builds with quad
+    step = (E[-1] - E[0]) / (len(E) - 1)
+    e_or, b_or = oracle.planck_sample(n, 123, 2025, cdf, np.float32(E[0] / E0), np.float32(step / E0))
+    b = b.cpu().numpy()
+    e = e.cpu().numpy()
+    assert np.array_equal(b, b_or)  # integer result: bit-exact
+    assert np.array_equal(np.isnan(e), b < 0) and _u().same_bits(e[b >= 0], e_or[b >= 0])
+    ok = b >= 0
+    np.testing.assert_allclose(e[ok].astype(np.float64) * E0, E[b[ok]], rtol=1e-6)  # grid energies
+    # chi-square of the bin histogram against the reference's bin masses (bins coarsened to >= 5 expected)
+    ncdf = cdf.size
+    counts = np.bincount(b[ok], minlength=ncdf)  # counts[x]: photons that got grid energy E[x], x = 1..ncdf-1
+    expected = norm * n  # mass of interval x; interval 0 is the reference's "None" branch
+    groups_c, groups_e, cc, ee = [], [], 0.0, 0.0
+    for ci, ei in zip(counts[1:ncdf], expected[1:ncdf]):
+        cc, ee = cc + ci, ee + ei
+        if ee >= 5:
+            groups_c.append(cc), groups_e.append(ee)
+            cc, ee = 0.0, 0.0
+    chi2 = float(((np.array(groups_c) - np.array(groups_e)) ** 2 / np.array(groups_e)).sum())
+    p = stats.chi2.sf(chi2, len(groups_c) - 1)
+    assert p > 1e-4, (chi2, len(groups_c), p)
+    assert abs((b < 0).mean() - norm[0]) < 5 * np.sqrt(norm[0] / n) + 1e-6  # None rate = mass of interval 0
+
+
+# ---------------------------------------------------------------------------------------------
+# stochastic parity: the reference's distributions (KS / chi-square at fixed sample size)
+# ---------------------------------------------------------------------------------------------
+def test_scatter_direction_distribution_matches_reference_law(ctx):
+    """The reference draws theta ~ U[0,2pi) as polar and phi ~ U[0,pi) as azimuth (light.py:285,
+    :309-311): v_z/c = cos(theta) is arcsine distributed, v_y >= 0 always scatters to sin(theta)
+    sign.  KS against those laws at n = 10^6; scattered fraction against pcoll (binomial)."""
+    from scipy import stats
+
+    u = _u()
+    n = 1_000_000
+    r, v = u.beam_photons(n)
+    st, g = u.make_store(ctx, r, v)
+    dt, c = 1e-3, u.C_LIGHT
+    k = 0.5 / (c * dt)  # pcoll = 0.5
+    row = u.photon_step(ctx, st, g, dt, k, c, 0, seed=77, step=0)
+    raw = [g.download(nm) for nm in ("vx", "vy", "vz")]
+    hit = ~((raw[0] == np.float32(c)) & (raw[1] == 0.0) & (raw[2] == 0.0))
+    vx, vy, vz = (a.astype(np.float64) / c for a in raw)
+    nh = int(hit.sum())
+    assert nh == int(row[4])
+    assert abs(nh - 0.5 * n) < 5 * np.sqrt(n * 0.25)
+    ks_z = stats.kstest(vz[hit], lambda t: 0.5 + np.arcsin(np.clip(t, -1, 1)) / np.pi)
+    assert ks_z.pvalue > 1e-3, ks_z
+    # phi = atan2(vy, vx) folded: uniform on [0, pi) after undoing the sign of sin(theta)
+    phi = np.arctan2(np.abs(vy[hit]), vx[hit] * np.sign(vy[hit] + (vy[hit] == 0)))
+    ks_p = stats.kstest(phi / np.pi, "uniform")
+    assert ks_p.pvalue > 1e-3, ks_p
+    assert np.abs(np.sqrt(vx[hit] ** 2 + vy[hit] ** 2 + vz[hit] ** 2) - 1).max() < 1e-6
+    # same statistics from the float64 reference law driven by the same Philox uniforms
+    ut, up, ur = oracle.philox_uniforms(n, 0, 77, 0)
+    rt, rp = law.scale_uniforms(ut.astype(np.float64), up.astype(np.float64))
+    ref_vz = np.cos(rt)[ur.astype(np.float64) <= 0.5 * (1 + 1e-7)]
+    assert stats.ks_2samp(vz[hit], ref_vz).pvalue > 1e-3
+
+
+def test_beer_lambert_survival(ctx):
+    """Delete scattering: survivors after s steps follow (1 - pcoll)^s (the physics behind the
+    reference's test_scatter_delete, test/test_light.py:45-66), checked per step at 5 sigma."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 1_000_000
+    r, v = u.beam_photons(n)
+    st, g = u.make_store(ctx, r, v)
+    dt, c = 1e-3, u.C_LIGHT
+    p = 1e-3 * 1e-3 * c * dt  # A n c dt of the reference test
+    alive = n
+    for step in range(12):
+        row = u.photon_step(ctx, st, g, dt, np.float32(1e-6), c, _capi.SCATTER_DELETE, seed=5, step=step)
+        assert row[_capi.T_LIVE_IN] == alive
+        expect = alive * (1 - p)
+        assert abs(row[_capi.T_ALIVE] - expect) < 5 * np.sqrt(alive * p * (1 - p)) + 1
+        assert row[_capi.T_ALIVE] + row[_capi.T_ABSORBED] == alive
+        alive = int(row[_capi.T_ALIVE])
+
+
+# ---------------------------------------------------------------------------------------------
+# gravity (new step; oracle from the definition, float64)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 513, 3000])
+def test_gravity_matches_float64_definition(ctx, n):
+    rng = np.random.default_rng(n)
+    pos = rng.normal(size=(3, n))
+    m = rng.uniform(0.5, 1.5, n)
+    G, eps2 = 1.0, 1e-4
+    posm = torch.from_numpy(np.ascontiguousarray(np.vstack([pos, m[None]]).T, np.float32)).cuda()
+    acc = torch.zeros((3, n), dtype=torch.float32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(G), C.c_float(eps2),
+             p(acc[0]), p(acc[1]), p(acc[2]), 0)
+    torch.cuda.synchronize()
+    pos32 = posm[:, :3].T.cpu().numpy().astype(np.float64)
+    m32 = posm[:, 3].cpu().numpy().astype(np.float64)
+    want = oracle.gravity_f64(np.ascontiguousarray(pos32), np.ascontiguousarray(m32), G, eps2)
+    got = acc.cpu().numpy().astype(np.float64)
+    scale = np.abs(want).max() if n > 1 else 1.0
+    assert np.abs(got - want).max() <= 1e-5 * scale + 1e-12
+    if n > 1:
+        # Newton's third law: total force vanishes to rounding
+        f = (got * m32[None]).sum(1)
+        assert np.abs(f).max() <= 1e-4 * np.abs(got * m32[None]).sum(1).max()
+
+
+def test_gravity_split_blocks_equal_whole(ctx):
+    """Sharded accumulation (local block, then remote blocks with accumulate=1) equals one pass."""
+    n = 2048
+    rng = np.random.default_rng(1)
+    posm = torch.from_numpy(np.ascontiguousarray(np.vstack([rng.normal(size=(3, n)), np.ones((1, n))]).T, np.float32)).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    whole = torch.zeros((3, n), dtype=torch.float32, device="cuda")
+    ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(1.0), C.c_float(1e-4),
+             p(whole[0]), p(whole[1]), p(whole[2]), 0)
+    parts = torch.zeros((3, n), dtype=torch.float32, device="cuda")
+    for b in range(4):
+        blk = posm[b * 512:(b + 1) * 512]
+        ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(blk), C.c_uint64(512), C.c_float(1.0), C.c_float(1e-4),
+                 p(parts[0]), p(parts[1]), p(parts[2]), int(b > 0))
+    torch.cuda.synchronize()
+    w, q = whole.cpu().numpy(), parts.cpu().numpy()
+    assert np.abs(w - q).max() <= 2e-5 * np.abs(w).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer entry point
+# ---------------------------------------------------------------------------------------------
+def test_host_buffer_step_equals_device_step(ctx):
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 300_007
+    r, v = u.random_photons(n, seed=21)
+    st, g = u.make_store(ctx, r, v)
+    host = {nm: torch.from_numpy(g.download(nm).copy()).pin_memory() for nm in u.PLANE_NAMES}
+    dt, k, c, r2 = 1e-3, 1.5e-6, u.C_LIGHT, 4.5e5 ** 2
+    for step in range(3):
+        want = u.photon_step(ctx, st, g, dt, k, c, 0, seed=9, step=step, r2_escape=r2, planes=[(1, 0.0)])
+        soa = _capi.Soa()
+        soa.n = n
+        for nm in u.PLANE_NAMES:
+            setattr(soa, nm, host[nm].data_ptr())
+        sp = _capi.ScatterParams(k=k, c=c, mode=0)
+        rg = _capi.Rng(seed=9, step=step)
+        pl = _capi.make_planes([(1, 0.0)])
+        row = np.zeros(_capi.TALLY_COLS, np.int64)
+        ctx.call("pcl_photon_step_host", C.byref(soa), C.c_float(dt), C.byref(sp), C.byref(rg), C.c_float(r2), C.byref(pl),
+                 row.ctypes.data_as(C.c_void_p), C.c_uint64(65_536))
+        assert np.array_equal(row, want)
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(host[nm].numpy(), g.download(nm)), nm
+
+
+def test_errors_are_reported_not_swallowed(ctx):
+    from physicl_b200 import _capi
+
+    soa = _capi.Soa()
+    soa.n = 16
+    with pytest.raises(_capi.PclError, match="r and v planes"):
+        ctx.call("pcl_kinematics", None, C.byref(soa), C.c_float(1.0), 0, None)
+    with pytest.raises(_capi.PclError):
+        _capi.Context(4096)

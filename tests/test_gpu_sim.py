@@ -1,0 +1,219 @@
+"""GPU tests through the public API (``Simulation`` / ``Step``), written like the reference's own
+tests (test/test_light.py) plus drop-in checks against its golden vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+import physicl_b200 as phys  # noqa: E402
+import physicl_b200.light  # noqa: E402
+import physicl_b200.newton  # noqa: E402
+from physicl_b200 import _capi  # noqa: E402
+
+
+def rand_ray():  # reference test/test_light.py:12-17
+    return {"s": np.array([0] * 3, dtype=np.double), "v": np.array([phys.light.c, 0, 0], dtype=np.double), "E": np.double(1)}
+
+
+def sim(n=10000, **kw):  # reference test/test_light.py:19-24
+    s = phys.Simulation(bounds=np.array([1000, 1000, 1000]), cl_on=True, exit=lambda cond: cond.t >= 0.100, **kw)
+    for _ in range(n):
+        s.add_obj(phys.light.PhotonObject(**rand_ray()))
+    return s
+
+
+def test_scatter_spherical():
+    """reference test/test_light.py:27-43, unchanged apart from the import."""
+    x = sim()
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(0.001), n=np.double(0.001)))
+    step = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(3, step)
+    x.start()
+    x.join()
+    assert len(step.data) == 100 and step.data[0][1] == 10000
+    error = (np.double(step.data[0][1] * 0.5) - (sum([y[2] for y in step.data]) / len(step.data))) / np.double(step.data[0][1] * 0.5)
+    assert np.isclose(error, 0, 0, 0.10)
+    # sharper than the reference's 10 %: late rows have forgotten the +x start
+    late = np.array([y[2] for y in step.data[50:]])
+    assert abs(late.mean() / 10000 - 0.5) < 0.02
+
+
+def test_scatter_delete():
+    """reference test/test_light.py:45-66 (including its row-2 quirk), then the
+    Beer-Lambert statement it was after."""
+    x = sim()
+    x.exit = lambda x: len(x.objects) == 0
+    N_i = len(x.objects)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    n, A = 0.001, 0.001
+    x.add_step(2, phys.light.ScatterDeleteStep(np.double(n), np.double(A)))
+    step = phys.light.ScatterMeasureStep(None, True, [[1 / (n * A), np.nan, np.nan]])
+    x.add_step(3, step)
+    x.start()
+    x.join()
+    N_x = sum(step.data[2])
+    error = (np.e ** -1 - (N_x / N_i)) / (np.e ** -1)
+    assert np.isclose(error, 0, 0, 0.10)
+    alive = np.array([r[1] for r in step.data])
+    assert np.all(np.diff(alive) <= 0) and alive[-1] == 0
+    p = n * A * float(phys.light.c) * 0.001
+    for s in range(6):
+        assert abs(alive[s] / N_i - (1 - p) ** (s + 1)) < 0.02
+    # the plane x = 1/(nA) is crossed on step 4 by everything still alive
+    assert step.data[3][2] == alive[3] and sum(r[2] for r in step.data) == alive[3]
+
+
+def test_numpy_rng_mode_reproduces_the_reference_run(golden):
+    """Drop-in check: same seed, same host RNG stream, same pipeline as the reference run that made
+    tests/golden/iso.npz -> identical measure-step rows."""
+    g = golden("iso")
+    N = int(g["N"])
+    np.random.seed(int(g["seed"]))
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= int(g["nsteps"]))
+    for _ in range(N):
+        x.add_obj(phys.light.PhotonObject(**rand_ray()))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(g["A"]), n=np.double(g["n"]), rng="numpy"))
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    plane = phys.light.ScatterMeasureStep(None, True, [np.array(p) for p in g["planes"]])
+    x.add_step(3, sign)
+    x.add_step(4, plane)
+    x.start()
+    x.join()
+    got_s, got_p = np.array(sign.data), np.array(plane.data)
+    assert np.array_equal(got_s[:, 1:], g["sign_rows"][:, 1:])
+    assert np.array_equal(got_p[:, 1:], g["plane_rows"][:, 1:])
+    np.testing.assert_allclose(got_s[:, 0], g["sign_rows"][:, 0], rtol=1e-12)
+    # final particle state against the reference's objects (pulls the store back into sim.objects)
+    last = int(g["nsteps"]) - 1
+    v = np.array([np.asarray(o.v, float) for o in x.objects]).T
+    r = np.array([np.asarray(o.r, float) for o in x.objects]).T
+    c = float(g["c"])
+    assert np.abs(v - g["s%d_v" % last]).max() <= 1e-5 * c
+    assert np.abs(r - g["s%d_r" % last]).max() <= 1e-5 * c * 0.001 * (last + 1)
+
+
+def test_numpy_rng_delete_reproduces_the_reference_run(golden):
+    g = golden("delete")
+    np.random.seed(int(g["seed"]))
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= int(g["nsteps"]))
+    for _ in range(int(g["N"])):
+        x.add_obj(phys.light.PhotonObject(**rand_ray()))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterDeleteStep(np.double(g["n"]), np.double(g["A"]), rng="numpy"))
+    plane = phys.light.ScatterMeasureStep(None, True, [np.array(g["planes"][0])])
+    x.add_step(3, plane)
+    x.start()
+    x.join()
+    assert np.array_equal(np.array(plane.data)[:, 1:], g["plane_rows"][:, 1:])
+    assert len(x.objects) == int(g["plane_rows"][-1][1])
+
+
+def _pipeline(fuse, n=20000, steps=30, seed=5):
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= steps, fuse=fuse, seed=seed)
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x.add_particles(r, v, E=np.ones(n))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(0.001), n=np.double(0.001)))
+    esc = phys.light.EscapeSphereStep(1.0e6)
+    x.add_step(3, esc)
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    plane = phys.light.ScatterMeasureStep(None, True, [[2.0e5, np.nan, np.nan], [np.nan, np.nan, 0.0]])
+    x.add_step(4, sign)
+    x.add_step(5, plane)
+    x.start()
+    x.join()
+    return x, esc, sign, plane
+
+
+def test_fused_and_unfused_pipelines_agree_exactly():
+    a, esc_a, sign_a, plane_a = _pipeline(True)
+    b, esc_b, sign_b, plane_b = _pipeline(False)
+    assert np.array_equal(np.array(sign_a.data), np.array(sign_b.data))
+    assert np.array_equal(np.array(plane_a.data), np.array(plane_b.data))
+    assert np.array_equal(esc_a.escaped, esc_b.escaped)
+    assert esc_a.escaped.sum() + sign_a.data[-1][1] == 20000 and esc_a.escaped.sum() > 0
+    assert len(a.objects) == sign_a.data[-1][1]
+    sa, sb = a.store.snapshot("photon"), b.store.snapshot("photon")
+    assert np.array_equal(sa["id"], sb["id"])
+    for nm in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(sa[nm].view(np.uint32), sb[nm].view(np.uint32)), nm
+    assert a.cl_ctx.launches < b.cl_ctx.launches  # one launch per timestep instead of five
+
+
+def test_mixed_population_and_host_step_interop():
+    """Kinematics moves every object, scattering touches photons only (light.py:283), the sign tally
+    counts all objects (light.py:423-426), and a user's host step sees current state."""
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 3)
+    for _ in range(50):
+        x.add_obj(phys.light.PhotonObject(**rand_ray()))
+    rocks = [phys.Object(v=phys.Measurement([0.0, -2.0, 3.0], "m**1 s**-1")) for _ in range(7)]
+    x.add_objs(rocks)
+    seen = []
+
+    class Peek(phys.Step):
+        def run(self, sim):
+            seen.append([np.asarray(o.r, float).copy() for o in sim.objects if type(o) is phys.Object])
+
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.5)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-8), n=np.double(1.0)))
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(3, sign)
+    x.add_step(4, Peek())
+    x.start()
+    x.join()
+    assert len(seen) == 3 and len(seen[0]) == 7
+    np.testing.assert_allclose(seen[2][0], [0.0, -3.0, 4.5], rtol=1e-6)
+    for row in sign.data:
+        assert row[1] == 57 and row[4] >= 7  # 7 rocks have v_z > 0, none has v_y > 0
+    assert all(type(o.v) is phys.Measurement for o in x.objects)
+
+
+def test_wavelength_law_with_the_references_rayleigh_constants():
+    """A = 5.1e-31 m^2 * (532 nm)^4 underflows binary32 and (h c / E)^-4 ~ 1e25 overflows the
+    product order of the reference kernel; the folded constant keeps the law exact."""
+    n = 200_000
+    rng = np.random.default_rng(3)
+    lam = rng.uniform(300e-9, 900e-9, n)
+    E = 6.62607015e-34 * 299792458.0 / lam
+    A, nd, dt = 5.1e-31 * (532e-9) ** 4, 2.5e25, 1e-5
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 1, seed=9)
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x.add_particles(r, v, E=E, track_nscat=True)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True))
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(3, sign)
+    x.start()
+    x.join()
+    pcoll = np.minimum(1.0, A * nd * 299792458.0 * dt * lam ** -4.0)
+    snap = x.store.snapshot("photon")
+    hits = snap["nscat"].astype(np.float64)
+    assert abs(hits.sum() - pcoll.sum()) < 5 * np.sqrt((pcoll * (1 - pcoll)).sum())
+    blue, red = lam < 450e-9, lam > 750e-9
+    assert hits[blue].mean() > 5 * hits[red].mean()  # lambda^-4
+    np.testing.assert_allclose(snap["E"], E, rtol=1e-6)
+
+
+def test_device_info_and_launch_accounting():
+    info = phys.Simulation.get_device_info()
+    dev = [v for k, v in info["physicl_b200"].items() if isinstance(v, dict)][0]
+    assert dev["MAX_COMPUTE_UNITS"] >= 100 and dev["GLOBAL_MEM_SIZE"] > 1e11
+    ctx = _capi.Context(0)
+    assert ctx.launches == 0
+    assert ctx.fp32_peak_tflops() > 20 and ctx.copy_peak_gbs(1 << 28) > 2000
+    assert ctx.launches > 0
+    ctx.close()

@@ -1,0 +1,362 @@
+"""CPU-only tests: host-side mirror of the reference API, the C-ABI surface, sharding logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import physicl_b200 as phys
+import physicl_b200.light
+import physicl_b200.newton
+from physicl_b200 import _capi, dist, fused
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- code units (behaviour of reference test/test_units.py) -----------------------------------
+def dict_equiv(a, b):
+    return all(b.get(k, 0) in (0, v) or v == 0 for k, v in a.items()) and all(a.get(k, 0) in (0, v) or v == 0 for k, v in b.items())
+
+
+def test_units_derived_equals_base():
+    x = phys.Measurement(5, "kg**1 m**1 s**-2")
+    y = phys.Measurement(5, "N**1")
+    assert x == y and x.units == y.units == {"M": 1, "L": 1, "T": -2}
+
+
+def test_units_scaling_au():
+    x = phys.Measurement(1, "au**1")
+    y = phys.Measurement(149597870700, "m**1")
+    assert x + y == phys.Measurement(2, "au**1")
+    assert y + x == phys.Measurement(149597870700 * 2, "m**1")
+
+
+def test_units_photon_object():
+    p = phys.light.PhotonObject(E=phys.Measurement(5, "J**1"), v=phys.Measurement([phys.light.c, 0, 0], "m**1 s**-1"))
+    assert p.E.units == {"L": 2, "T": -2, "M": 1}
+    assert p.v.units == {"L": 1, "T": -1}
+    assert np.linalg.norm(p.v) == phys.light.c
+    with pytest.raises(Exception, match="valid speed"):
+        phys.light.PhotonObject(E=1, v=phys.Measurement([1.0, 0, 0], "m**1 s**-1"))
+    with pytest.raises(Exception, match="valid energy"):
+        phys.light.PhotonObject(v=phys.Measurement([phys.light.c, 0, 0], "m**1 s**-1"))
+
+
+def test_units_wavelength_energy_roundtrip():
+    E = phys.light.E_from_wavelength(phys.Measurement(633e-9, "m**1"))
+    assert E == (299792458 * 6.62607015e-34) / (633e-9)
+    assert E.units == {"L": 2, "T": -2, "M": 1}
+    wv = phys.light.wavelength_from_E(E)
+    assert wv == 633e-9
+    assert dict_equiv(wv.units, {"L": 1})
+
+
+def test_units_ev_conversion():
+    E_g = phys.Measurement(0, "J**1") + phys.Measurement(13.6, "eV**1")
+    f = E_g / phys.light.h
+    lam = phys.light.c / f
+    assert E_g == 1.602176634e-19 * 13.6
+    assert f == (1.602176634e-19 * 13.6) / 6.62607015e-34 and dict_equiv(f.units, {"T": -1})
+    assert lam == 299792458 / ((1.602176634e-19 * 13.6) / 6.62607015e-34) and dict_equiv(lam.units, {"L": 1})
+
+
+def test_units_ufuncs():
+    a = phys.Measurement(5, "kg**1 m**1 s**-2")
+    l = phys.Measurement(5, "au**1")
+    t = phys.Measurement(10, "min**2")
+    assert a * t == 50
+    assert phys.Measurement(0, "kg**1 m**1") + (a * t) == (60 ** 2) * 10 * 5
+    assert a * l == 25
+    assert (a / l).flat[0] == 5 / (5 * 149597870700)
+    assert a ** 2 == 25
+    # sqrt carries half powers (the reference's unit parser drops them: its test_units_6 fails upstream)
+    assert float(np.sqrt(l)) == pytest.approx(np.sqrt(5 * 149597870700), rel=1e-15)
+    assert np.sqrt(l).units == {"L": 0.5}
+    assert float(phys.Measurement(0, "m**1") + np.sqrt(l)) == pytest.approx(np.sqrt(149597870700 * 5), rel=1e-15)
+    assert str(phys.light.c) == "299792458.0" and str(phys.light.h) == "6.62607015E-34"  # what kernels get spliced
+
+
+def test_code_scale_changes_constants():
+    import importlib
+
+    phys.Measurement.set_code_scale("m", 1e-3)
+    try:
+        assert float(phys.Measurement(1.0, "m**1")) == 1e-3
+        mod = importlib.reload(phys.light)
+        assert float(mod.c) == pytest.approx(299792.458)
+    finally:
+        phys.Measurement.reset_code_scale("m")
+        importlib.reload(phys.light)
+    assert float(phys.light.c) == 299792458.0
+
+
+# ---- Simulation runtime (physicl/__init__.py:400-541) -----------------------------------------
+class Recorder(phys.Step):
+    touches_objects = False
+
+    def __init__(self, log, tag):
+        self.log, self.tag, self.done = log, tag, False
+
+    def run(self, sim):
+        self.log.append(self.tag)
+
+    def terminate(self, sim):
+        self.done = True
+
+
+def test_simulation_runs_steps_in_insertion_order_until_exit():
+    log = []
+    s = phys.Simulation(cl_on=False, exit=lambda c: c.t >= 0.003)
+    s.add_step(3, phys.UpdateTimeStep(lambda c: np.double(0.001)))
+    a, b = Recorder(log, "a"), Recorder(log, "b")
+    s.add_step(1, b)
+    s.add_step(0, a)
+    s.start()
+    s.join()
+    assert log == ["b", "a"] * 3  # insertion order, not idx order
+    assert len(s.ts) == 3 and s.ts[-1] == pytest.approx(0.003) and not s.running and a.done and b.done
+    assert s.run_time >= 0
+
+
+def test_add_step_duplicate_and_remove_while_running():
+    s = phys.Simulation(cl_on=False)
+    s.add_step(0, phys.Step())
+    with pytest.raises(NameError):
+        s.add_step(0, phys.Step())
+    s.running = True
+    with pytest.raises(RuntimeError):
+        s.remove_step(0)
+    s.running = False
+    s.remove_step(0)
+    assert s.steps == {}
+
+
+def test_default_exit_and_object_list():
+    s = phys.Simulation(cl_on=False)
+    o = phys.Object()
+    s.add_obj(o)
+    s.add_objs([phys.Object(), phys.Object()])
+    assert len(s.objects) == 3 and not s.exit(s)
+    s.remove_obj(o)
+    assert len(s.objects) == 2 and s.get_state()["objects"] == 2
+
+    class Drop(phys.Step):
+        def run(self, sim):
+            sim.remove_obj(sim.objects[0])
+
+    s.add_step(0, Drop())
+    s.start()
+    s.join()
+    assert len(s.objects) == 0
+
+
+def test_step_errors_surface_on_join():
+    class Boom(phys.Step):
+        def run(self, sim):
+            raise ValueError("boom")
+
+    s = phys.Simulation(cl_on=False, exit=lambda c: False)
+    s.add_step(0, Boom())
+    s.start()
+    with pytest.raises(ValueError, match="boom"):
+        s.join()
+    assert not s.running
+
+
+def test_measure_step_writes_rows(tmp_path):
+    fn = tmp_path / "out.csv"
+    m = phys.MeasureStep(str(fn))
+    m.data.append(np.array([0.001, 10, 4]))
+    m.data.append(np.array([0.002, 9, 5]))
+    m.terminate(None)
+    lines = fn.read_text().strip().split("\n")
+    assert lines[0] == "0.001, 10.0, 4.0" and len(lines) == 2
+
+
+def test_device_steps_refuse_to_run_without_device():
+    s = phys.Simulation(cl_on=False, exit=lambda c: c.t >= 0.001)
+    s.add_obj(phys.Object())
+    s.add_step(0, phys.UpdateTimeStep(lambda c: np.double(0.001)))
+    s.add_step(1, phys.newton.NewtonianKinematicsStep())
+    s.start()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        s.join()
+
+
+def test_out_of_scope_features_say_so():
+    with pytest.raises(NotImplementedError):
+        phys.light.ScatterIsotropicStep(variable_n=True, variable_n_fn="1.0")
+    with pytest.raises(NotImplementedError):
+        phys.light.ScatterMeasureStep(None, True, [], measure_E=True)
+    with pytest.raises(NotImplementedError):
+        phys.light.TracePathMeasureStep(None)
+
+
+def test_fuse_plan_groups_the_canonical_pipeline():
+    upd = phys.UpdateTimeStep(lambda c: 1e-3)
+    kin = phys.newton.NewtonianKinematicsStep()
+    sc = phys.light.ScatterIsotropicStep(A=1e-3, n=1e-3)
+    esc = phys.light.EscapeSphereStep(3e6)
+    sign = phys.light.ScatterSignMeasureStep(None)
+    pl = phys.light.ScatterMeasureStep(None, True, [[1e6, np.nan, np.nan]])
+    user = Recorder([], "u")
+    plan = fused.fuse_plan([upd, kin, sc, esc, sign, pl, user])
+    assert plan[0] is upd and isinstance(plan[1], fused.FusedPhotonStep) and plan[2] is user and len(plan) == 3
+    assert plan[1].members == [kin, sc, esc, sign, pl] and plan[1]._planes.count == 1
+    # any other order stays unfused
+    plan2 = fused.fuse_plan([upd, sc, kin, sign])
+    assert plan2 == [upd, sc, kin, sign]
+    plan3 = fused.fuse_plan([kin, user, sc])
+    assert plan3 == [kin, user, sc]
+    acc = phys.newton.NewtonianKinematicsStep(accel=True, a_uniform=[0, 0, -9.81])
+    assert fused.fuse_plan([acc, sc]) == [acc, sc]
+
+
+def test_scatter_params_fold_constants_in_float64():
+    class G:
+        e0 = 9.93e-19
+
+    st = phys.light.ScatterIsotropicStep(A=np.double(5.1e-31 * (532e-9) ** 4), n=np.double(2.5e25), wavelength_dep_scattering=True)
+    sp = st.scatter_params(G())
+    hc = 6.62607015e-34 * 299792458.0
+    want = 5.1e-31 * (532e-9) ** 4 * 2.5e25 * (G.e0 / hc) ** 4
+    assert sp.mode == _capi.SCATTER_WAVELENGTH and sp.k == pytest.approx(want, rel=1e-6)
+    assert 1e-12 < sp.k < 1e-2  # representable in binary32 although A ~ 4e-56 is not
+    assert np.float32(5.1e-31 * (532e-9) ** 4) == 0.0
+
+
+# ---- emission host path -------------------------------------------------------------------------
+def test_planck_host_sampler_reproduces_reference_sequence(golden):
+    g = golden("planck")
+    np.random.seed(int(g["seed"]))
+    phys.light.last_planck_params = None
+    got = [phys.light.planck_phot_distribution(float(g["E_min"]), float(g["E_max"]), float(g["T"]), bins=int(g["bins"]))
+           for _ in range(len(g["E"]))]
+    none = np.array([v is None for v in got])
+    assert np.array_equal(none, np.isnan(g["E"])) and none.sum() > 0
+    vals = np.array([np.nan if v is None else float(v) for v in got])
+    assert np.array_equal(vals[~none], g["E"][~none])
+    np.testing.assert_allclose(phys.light.last_planck_cdf, g["cdf"], rtol=1e-11)
+    pr = phys.light.planck_probability(float(g["E_min"]), float(g["E_max"]), float(g["T"]))
+    assert 0 < pr[0] < 1
+
+
+def test_generate_photons_shapes():
+    ph = phys.light.generate_photons(5, min=1e-19, max=2e-19)
+    assert len(ph) == 5 and all(type(p) is phys.light.PhotonObject for p in ph)
+    assert all(1e-19 <= float(p.E) <= 2e-19 for p in ph)
+    assert np.array_equal(np.asarray(ph[0].v), [float(phys.light.c), 0, 0])
+    ph2 = phys.light.generate_photons_from_E([1.0, 2.0])
+    assert [float(p.E) for p in ph2] == [1.0, 2.0]
+
+
+# ---- C ABI surface ---------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, "include", "physicl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pcl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_capi.EXPORTS)
+    assert _capi.load().pcl_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_capi.Soa) == 8 + 15 * 8 + 8
+    assert ctypes.sizeof(_capi.ScatterParams) == 16
+    assert ctypes.sizeof(_capi.Rng) == 8 + 4 + 4 + 3 * 8
+    assert ctypes.sizeof(_capi.Planes) == 4 + 4 * 8 + 4 * 8
+    assert _capi.make_planes([(0, 1.0), (2, -3.5)]).count == 2
+    with pytest.raises(ValueError):
+        _capi.make_planes([(0, 0.0)] * 9)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    with pytest.raises(_capi.PclError, match="no CUDA device|failed"):
+        _capi.Context(0)
+    with pytest.raises(_capi.PclError):
+        phys.Simulation(cl_on=True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "physicl_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f
+
+
+# ---- sharding ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p", [(0, 4), (7, 8), (1000, 3), (16 * 2 ** 20, 8), (10 ** 9, 8)])
+def test_shard_range_partitions_exactly(n, p):
+    spans = [dist.shard_range(n, r, p) for r in range(p)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_oracle_steps_equal_unsharded():
+    """Why sharding needs no data-path collective: the Philox counter is the GLOBAL particle id, so
+    P independent shards reproduce the single-shard run bit for bit and tallies add up."""
+    import oracle
+
+    n, c, dt, k = 10_001, 299792458.0, 1e-3, 1.1e-6
+    rng = np.random.default_rng(0)
+    d = rng.normal(size=(3, n))
+    v = (c * d / np.linalg.norm(d, axis=0)).astype(np.float32)
+    base = {nm: a.copy() for nm, a in zip(("x", "y", "z", "vx", "vy", "vz"), list(np.zeros((3, n), np.float32)) + list(v))}
+    whole = {nm: a.copy() for nm, a in base.items()}
+    rows = [oracle.photon_step_f32(whole, dt, k, c, seed=3, step=s, r2_escape=np.float32(6e5 ** 2)) for s in range(4)]
+    for p in (2, 3, 8):
+        parts = []
+        tot = np.zeros((4, 16), np.int64)
+        for r in range(p):
+            lo, hi = dist.shard_range(n, r, p)
+            sh = {nm: a[lo:hi].copy() for nm, a in base.items()}
+            for s in range(4):
+                tot[s] += oracle.photon_step_f32(sh, dt, k, c, seed=3, step=s, r2_escape=np.float32(6e5 ** 2), id_base=lo)
+            parts.append(sh)
+        assert np.array_equal(tot, np.array(rows))
+        for nm in base:
+            assert np.array_equal(np.concatenate([q[nm] for q in parts]).view(np.uint32), whole[nm].view(np.uint32))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as td
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = dist.shard_range(1001)
+        rows = np.zeros((3, 16), np.int64)
+        rows[:, 0] = hi - lo
+        rows[:, 1] = rank + 1
+        total = dist.all_reduce_rows(rows)
+        q.put((rank, lo, hi, total.tolist(), dist.all_reduce_int(hi - lo)))
+    finally:
+        td.destroy_process_group()
+
+
+def test_gloo_world2_tally_reduction():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert [o[1:3] for o in out] == [(0, 501), (501, 1001)]
+    for o in out:
+        assert o[3][0][0] == 1001 and o[3][2][1] == 3 and o[4] == 1001
