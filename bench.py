@@ -164,15 +164,19 @@ def cpu_photon_sphere(n, steps, warmup):
     return live / dt, dt, oracle.num_threads()
 
 
-def cpu_baseline_block(budget_s=15.0):
-    """Bounded sample: 2 Mi photons, as many steps as fit ~budget_s (at least 3)."""
-    n = 2 * 2 ** 20
-    rate, dt, cores = cpu_photon_sphere(n, 2, 1)
-    steps = int(max(3, min(40, budget_s / max(dt / 2, 1e-3))))
-    rate, dt, cores = cpu_photon_sphere(n, steps, 1)
-    return {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d photons x %d steps of the photon_sphere workload, float64 reference law "
-                      "(oracle/c/oracle.c orc_photon_step_f64, OpenMP), %.1f s" % (n, steps, dt)}
+def cpu_baseline_block(steps, warmup, budget_s=12.0):
+    """Bounded sample: the same step window as the GPU arm over 4 Mi photons, repeated until about
+    budget_s seconds of CPU work have been timed."""
+    n = 4 * 2 ** 20
+    live_total, t_total, reps, cores = 0.0, 0.0, 0, 1
+    while t_total < budget_s and reps < 200:
+        rate, dt, cores = cpu_photon_sphere(n, steps, warmup)
+        live_total += rate * dt
+        t_total += dt
+        reps += 1
+    return {"value": live_total / t_total, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d photons x steps [%d, %d) of the photon_sphere workload, %d repetitions, float64 reference law "
+                      "(oracle/c/oracle.c orc_photon_step_f64, OpenMP), %.1f s timed" % (n, warmup, warmup + steps, reps, t_total)}
 
 
 def run_reference(args):
@@ -254,6 +258,8 @@ def bench_photon_sphere(args, rank, world, local):
     # ---- e2e: host buffers in, host buffers out, every step ---------------------------------
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         host = {k: torch.zeros(n, dtype=torch.float32).pin_memory() for k in ("x", "y", "z", "vx", "vy", "vz")}
         host["vx"].fill_(C_LIGHT)
         soa = _capi.Soa()
@@ -288,7 +294,7 @@ def bench_photon_sphere(args, rank, world, local):
     except Exception as e:  # report, never hide
         e2e = {"value": None, "unit": "particle-steps/s", "error": repr(e)}
 
-    cpu = cpu_baseline_block() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    cpu = cpu_baseline_block(args.steps, args.warmup) if (rank == 0 and world == 1 and not args.no_cpu) else None
     out = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -421,6 +427,7 @@ def main():
     ap.add_argument("--workload", default="photon_sphere_16m",
                     choices=["photon_sphere_16m", "kinematics_1m", "kinematics_64m", "kinematics_ref_64m", "gravity_256k"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -61,7 +61,19 @@ typedef struct pcl_soa {
     uint32_t *nscat;        /* scatter count per photon, nullable (stands in for the    */
                             /* dv!=0 counting of TracePathMeasureStep, light.py:459-460)*/
     uint64_t id_base;       /* global id = id_base + local id (RNG counter, sharding)   */
+    const uint64_t *n_dev;  /* nullable DEVICE pointer: when set, the number of valid   */
+                            /* slots is min(n, *n_dev), read by the kernel, so stepping  */
+                            /* loops that retire photons never wait for the host         */
 } pcl_soa;
+
+/* Two SoA buffers used alternately by the retire-and-compact step, plus their device-side slot
+ * counts.  buf[cur] holds the photons; n_dev[k] is the valid-slot count of buf[k]. */
+typedef struct pcl_pingpong {
+    pcl_soa buf[2];
+    uint64_t *n_dev;   /* device uint64[2] */
+    uint32_t cur;      /* 0 or 1 */
+    uint32_t id_valid; /* bit k: buf[k].id holds real ids; otherwise the id of a slot is its index */
+} pcl_pingpong;
 
 /* Scatter law of light_scatter_step_sphere / light_scatter_step_del
  * (physicl/light.py:303-315, :146-158, :239-249). */
@@ -141,6 +153,23 @@ int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
 int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                      const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                      const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps);
+
+/* Same timestep, with Simulation.remove_obj (physicl/__init__.py:455-459) folded in: photons are read
+ * from `src` and the SURVIVORS are written densely to `dst` (out of place; dst needs r, v, id and
+ * whatever optional planes src has), so retired photons cost nothing from the next step on.
+ * Survivors keep their order inside a 1024-slot tile; tiles land in arrival order, ids identify
+ * photons.  n_out_dev: device uint64 receiving the survivor count (zeroed by the call). */
+int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_soa *dst,
+                            float dt, const pcl_scatter_params *sp, const pcl_rng *rng,
+                            float escape_r2, const pcl_planes *planes, int64_t *tally_row,
+                            uint64_t *n_out_dev);
+/* nsteps fused steps over a ping-pong pair: step s runs in place, except that every step with
+ * (rng->step + s + 1) % compact_every == 0 is a retire-and-compact step (compact_every = 0: never).
+ * pp->cur and the upper bounds pp->buf[].n are updated; exact counts stay on the device. */
+int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float dt,
+                        const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                        const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps,
+                        uint32_t compact_every);
 
 /* ScatterSignMeasureStep.run / ScatterMeasureStep.run as stand-alone device tallies
  * (light.py:414-431, :374-404).  Adds into tally_row[PCL_TALLY_COLS] (caller zeroes). */

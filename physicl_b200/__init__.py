@@ -173,7 +173,8 @@ class Simulation(threading.Thread):
         self.seed = 0
         self.fuse = True
         self.shard = False
-        self.compact_every = 16  # timesteps between live-count checks of the fused photon step
+        self.compact_every = 16  # timesteps between host live-count syncs of the fused photon step
+        self.compact_cadence = None  # every m-th timestep retires-and-compacts; None = adaptive
         for attr, val in kwargs.items():
             setattr(self, attr, val)
         self.dt = Measurement(np.double(0), "s**1")
@@ -395,7 +396,33 @@ class Simulation(threading.Thread):
         plan = self._plan()
         if not self.ts:
             self.t, self.dt = 0, 0
-        for _ in range(int(nsteps)):
+        nsteps = int(nsteps)
+        # bulk form: [UpdateTimeStep, fused photon step] with a constant dt goes to the device in
+        # chunks of up to compact_every timesteps per C-ABI call
+        if (len(plan) == 2 and type(plan[0]) is UpdateTimeStep and hasattr(plan[1], "run_many")
+                and plan[1].can_run_many(self)):
+            upd, fused = plan
+            while nsteps > 0:
+                room = self.compact_every - self.step_index % self.compact_every if self.compact_every else 64
+                k = min(nsteps, room, 256)
+                dts, ts = [], []
+                for _ in range(k):
+                    upd.run(self)
+                    dts.append(float(self.dt))
+                    ts.append(self.t)
+                    if dts[-1] != dts[0]:
+                        break
+                if dts[-1] != dts[0]:  # dt changed inside the chunk: finish these steps one by one
+                    for dt_i, t_i in zip(dts, ts):
+                        fused.run_many(self, 1, dt_i, [t_i])
+                        self.step_index += 1
+                    nsteps -= len(dts)
+                    continue
+                fused.run_many(self, k, dts[0], ts)
+                self.step_index += k
+                nsteps -= k
+            return
+        for _ in range(nsteps):
             for step in plan:
                 if not step.uses_device and getattr(step, "touches_objects", True):
                     self._pull_objects()

@@ -26,7 +26,12 @@ class PclError(RuntimeError):
 
 class Soa(C.Structure):
     _fields_ = [("n", C.c_uint64)] + [(k, C.c_void_p) for k in (
-        "x", "y", "z", "vx", "vy", "vz", "dx", "dy", "dz", "ax", "ay", "az", "e", "id", "nscat")] + [("id_base", C.c_uint64)]
+        "x", "y", "z", "vx", "vy", "vz", "dx", "dy", "dz", "ax", "ay", "az", "e", "id", "nscat")] + [("id_base", C.c_uint64),
+                                                                                                  ("n_dev", C.c_void_p)]
+
+
+class Pingpong(C.Structure):
+    _fields_ = [("buf", Soa * 2), ("n_dev", C.c_void_p), ("cur", C.c_uint32), ("id_valid", C.c_uint32)]
 
 
 class ScatterParams(C.Structure):
@@ -69,6 +74,8 @@ _PROTOS = {
     "pcl_escape": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_void_p]),
     "pcl_photon_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p]),
     "pcl_photon_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint32]),
+    "pcl_photon_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_void_p]),
+    "pcl_photon_steps_pp": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Pingpong), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint32, C.c_uint32]),
     "pcl_tally": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Planes), C.c_void_p]),
     "pcl_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Soa), C.c_void_p]),
     "pcl_planck_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

@@ -125,6 +125,7 @@ extern "C" int pcl_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, c
     PCL_REQUIRE(ctx, dst->x && dst->y && dst->z && dst->vx && dst->vy && dst->vz && dst->id,
                 "dst needs r, v and id planes");
     PCL_REQUIRE(ctx, dst->x != src->x, "compaction is out of place");
+    PCL_REQUIRE(ctx, src->n_dev == nullptr, "compaction needs the exact slot count on the host (n_dev must be null)");
     PCL_REQUIRE(ctx, src->n < (1ull << 32), "a shard holds fewer than 2^32 slots");
     PCL_REQUIRE(ctx, pcl_aligned16(src->x), "src x plane must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;

@@ -9,9 +9,10 @@
 // lane reads the same j-body (LDS.128 broadcast, conflict-free).
 // Per interaction: 3 FADD + 3 FFMA + 1 MUFU.RSQ + 3 FMUL + 3 FFMA = 12 FP32-pipe ops + 1 SFU op,
 // counted as 20 FLOP (the customary all-pairs figure).
+#include <stdlib.h>
+
 #include "pcl_common.cuh"
 
-#define GRAV_THREADS 128
 #define GRAV_JT 256
 
 __device__ __forceinline__ float pcl_rsqrt_approx(float x) {
@@ -30,7 +31,7 @@ __device__ __forceinline__ void pcl_cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
-template <int IB>
+template <int IB, int GRAV_THREADS>
 __global__ void __launch_bounds__(GRAV_THREADS)
 pcl_k_gravity(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__restrict__ pj, uint64_t n_total,
               float G, float eps2, float *ax, float *ay, float *az, int accumulate) {
@@ -110,10 +111,28 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
     PCL_REQUIRE(ctx, pcl_aligned16(posm_local) && pcl_aligned16(posm_all), "posm arrays must be 16-byte aligned");
     PCL_REQUIRE(ctx, eps2 > 0.f, "softening eps2 must be > 0 (the i == j term relies on it)");
     if (n_local == 0 || n_total == 0) return 0;
-    constexpr int IB = 4;
-    unsigned grid = (unsigned)((n_local + GRAV_THREADS * IB - 1) / (GRAV_THREADS * IB));
-    pcl_k_gravity<IB><<<grid, GRAV_THREADS, 0, (cudaStream_t)stream>>>(
-        (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate);
+    // Tile shape: IB i-bodies per thread x T threads per CTA.  Small CTAs keep the number of CTAs per
+    // SM nearly uniform (262144 bodies -> 1024 CTAs of 256 bodies: 6.9 per SM), which matters because
+    // every CTA does the same amount of work and the kernel is issue-bound.
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("PCL_GRAV_VARIANT");  // tuning aid; default chosen from ncu/bench data
+        variant = e ? atoi(e) : 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+#define PCL_GRAV(IB, T)                                                                                       \
+    pcl_k_gravity<IB, T><<<(unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), T, 0, st>>>(                  \
+        (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
+    switch (variant) {
+        case 1: PCL_GRAV(4, 128); break;
+        case 2: PCL_GRAV(2, 128); break;
+        case 3: PCL_GRAV(2, 64); break;
+        case 4: PCL_GRAV(8, 64); break;
+        case 5: PCL_GRAV(8, 32); break;
+        case 6: PCL_GRAV(4, 32); break;
+        default: PCL_GRAV(4, 64); break;
+    }
+#undef PCL_GRAV
     PCL_LAUNCHED(ctx);
     return 0;
 }

@@ -7,8 +7,9 @@
 // the SMs all stay busy.  Bytes over PCIe per photon-step: 24 B up (r, v) + 24 B down (+4 B e up).
 #include "pcl_common.cuh"
 
-int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, const pcl_scatter_params *sp,
-                         const pcl_rng *rng, float escape_r2, const pcl_planes *planes, int64_t *tally_row);
+int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
+                         const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                         int64_t *tally_row, uint64_t *n_out);
 
 #define PIPE_SLOTS 3
 #define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
@@ -109,7 +110,7 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
                 r.u_phi = b[10];
             }
         }
-        rc = pcl_photon_step_impl(ctx, st, &d, dt, sp, &r, escape_r2, planes, hp->tally_dev);
+        rc = pcl_photon_step_impl(ctx, st, &d, nullptr, dt, sp, &r, escape_r2, planes, hp->tally_dev, nullptr);
         if (rc) return rc;
         float *dst[6] = {host->x, host->y, host->z, host->vx, host->vy, host->vz};
         for (int q = 0; q < 6; ++q)

@@ -117,6 +117,7 @@ static int launch_kin(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, float dt,
 static int kin_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, int accel,
                         const float *a_uniform) {
     PCL_REQUIRE(ctx, p != nullptr, "null particle view");
+    PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
     const bool dr = p->dx != nullptr;

@@ -124,16 +124,57 @@ static_assert((int)C_ALIVE == (int)PCL_T_ALIVE && (int)C_XP == (int)PCL_T_XP && 
               "register tally layout must match the ABI row layout");
 
 // ---------------------------------------------------------------------------------------------
-// Fused photon step, 4 photons per thread.
+// One photon, one timestep: kinematics -> scatter -> escape -> tallies.  Shared by every fused kernel.
+// On return x is NaN if the photon retired; v holds the new direction if it scattered.
+// ---------------------------------------------------------------------------------------------
+template <bool WAVE, bool DEL, int NC>
+__device__ __forceinline__ uint32_t pcl_photon_one(const StepK &K, float &x, float &y, float &z, float &vx, float &vy,
+                                                   float &vz, float e, float ut, float up, float ur,
+                                                   uint32_t (&cnt)[NC]) {
+    cnt[C_LIVEIN] += 1u;
+    float dx = vx * K.dt, dy = vy * K.dt, dz = vz * K.dt;
+    float xx = x + dx, yy = y + dy, zz = z + dz;
+    uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz);
+    if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
+        float r2 = xx * xx;
+        r2 = fmaf(yy, yy, r2);
+        r2 = fmaf(zz, zz, r2);
+        if (r2 >= K.r2_escape) f |= F_ESCAPED;
+    }
+    cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
+    cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
+    cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
+    if (f & (F_ABSORBED | F_ESCAPED)) {
+        xx = __int_as_float(0x7fc00000);
+    } else {
+        pcl_tally_one(K, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
+    }
+    x = xx;
+    y = yy;
+    z = zz;
+    return f;
+}
+
+// number of valid slots: the view's n, or the device-resident count when the caller keeps it there
+__device__ __forceinline__ uint64_t pcl_valid_slots(const pcl_soa &p) {
+    if (p.n_dev) {
+        uint64_t nd = *p.n_dev;
+        return nd < p.n ? nd : p.n;
+    }
+    return p.n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused photon step, in place, 4 photons per thread.
 // ---------------------------------------------------------------------------------------------
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK)
-pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row, uint64_t nvec) {
+pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     uint32_t cnt[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) cnt[q] = 0u;
-    const float qnan = __int_as_float(0x7fc00000);
+    const uint64_t nvec = pcl_valid_slots(p) / 4;
     const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
     for (uint64_t g = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; g < nvec; g += stride) {
         const uint64_t i = g * 4;
@@ -155,13 +196,7 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row, uint64_t nvec) {
         if (p.nscat) nsc = pcl_ld4u(p.nscat + i);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-            float xx = pcl_f4(x, l);
-            if (xx != xx) continue;  // retired slot
-            cnt[C_LIVEIN] += 1u;
-            float dx = pcl_f4(vx, l) * K.dt, dy = pcl_f4(vy, l) * K.dt, dz = pcl_f4(vz, l) * K.dt;
-            xx = xx + dx;
-            float yy = pcl_f4(y, l) + dy;
-            float zz = pcl_f4(z, l) + dz;
+            if (pcl_f4(x, l) != pcl_f4(x, l)) continue;  // retired slot
             float ut, up, ur;
             if (INJ) {
                 ut = pcl_f4(ut4, l);
@@ -171,29 +206,12 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row, uint64_t nvec) {
                 uint64_t gid = p.id_base + (has_id ? (uint64_t)pcl_u4(id, l) : (i + (uint64_t)l));
                 pcl_draw(K, gid, ut, up, ur);
             }
-            uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, pcl_f4(e, l), ut, up, ur, K.k, K.c,
-                                                    pcl_f4(vx, l), pcl_f4(vy, l), pcl_f4(vz, l));
-            if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
-                float r2 = xx * xx;
-                r2 = fmaf(yy, yy, r2);
-                r2 = fmaf(zz, zz, r2);
-                if (r2 >= K.r2_escape) f |= F_ESCAPED;
-            }
-            cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
-            cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
-            cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
+            uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                   pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut, up, ur, cnt);
             if (!DEL && (f & F_SCATTERED)) {
                 any_scat = 1u;
                 pcl_u4(nsc, l) += 1u;
             }
-            if (f & (F_ABSORBED | F_ESCAPED)) {
-                xx = qnan;
-            } else {
-                pcl_tally_one(K, xx, yy, zz, dx, dy, dz, pcl_f4(vx, l), pcl_f4(vy, l), pcl_f4(vz, l), cnt);
-            }
-            pcl_f4(x, l) = xx;
-            pcl_f4(y, l) = yy;
-            pcl_f4(z, l) = zz;
         }
         pcl_st4(p.x + i, x);
         pcl_st4(p.y + i, y);
@@ -208,58 +226,160 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row, uint64_t nvec) {
     pcl_flush_tally(cnt, row, K.nplanes);
 }
 
-// scalar form: tails, unaligned views
+// scalar form: the n % 4 tail, and views that are not 16-byte aligned
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK)
-pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, uint64_t begin, uint64_t end) {
+pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     uint32_t cnt[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) cnt[q] = 0u;
-    const float qnan = __int_as_float(0x7fc00000);
-    uint64_t i = begin + (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x;
-    if (i < end) {
-        float xx = p.x[i];
-        if (xx == xx) {
-            cnt[C_LIVEIN] += 1u;
-            float vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
-            float dx = vx * K.dt, dy = vy * K.dt, dz = vz * K.dt;
-            xx = xx + dx;
-            float yy = p.y[i] + dy, zz = p.z[i] + dz;
+    const uint64_t end = pcl_valid_slots(p);
+    const uint64_t begin = aligned ? (end / 4) * 4 : 0;
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < end; i += stride) {
+        float x = p.x[i];
+        if (x != x) continue;
+        float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+        float ut, up, ur;
+        if (INJ) {
+            ut = K.u_theta[i];
+            up = K.u_phi[i];
+            ur = K.u_rand[i];
+        } else {
+            uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
+            pcl_draw(K, gid, ut, up, ur);
+        }
+        uint32_t f = pcl_photon_one<WAVE, DEL>(K, x, y, z, vx, vy, vz, WAVE ? p.e[i] : 1.f, ut, up, ur, cnt);
+        p.x[i] = x;
+        p.y[i] = y;
+        p.z[i] = z;
+        if (!DEL && (f & F_SCATTERED)) {
+            p.vx[i] = vx;
+            p.vy[i] = vy;
+            p.vz[i] = vz;
+            if (p.nscat) p.nscat[i] += 1u;
+        }
+    }
+    pcl_flush_tally(cnt, row, K.nplanes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused photon step with retirement folded in: reads the live photons of `s`, writes the survivors
+// densely into `d` (ping-pong partner), so the next step touches live photons only and a warp never
+// spends bandwidth or issue slots on retired ones.  Survivors of a 1024-slot tile keep their order
+// (ballot-free: 4-bit masks, shuffle scan, one atomic range reservation per tile); tiles land in
+// reservation order, which is why ids travel with the photons (RNG counter, identity).
+// Traffic per live photon-step: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
+// ---------------------------------------------------------------------------------------------
+template <bool WAVE, bool DEL, bool INJ, bool PL>
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned long long *n_out) {
+    constexpr int NC = PL ? C_N : C_PLANE0;
+    __shared__ uint32_t s_warp[PCL_WARPS];
+    __shared__ unsigned long long s_base;
+    uint32_t cnt[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    const uint64_t n = pcl_valid_slots(s);
+    const uint64_t ntiles = (n + PCL_BLOCK * 4 - 1) / (PCL_BLOCK * 4);
+    const bool has_id = s.id != nullptr;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t i = (tile * PCL_BLOCK + threadIdx.x) * 4;
+        float4 x, y, z, vx, vy, vz, e = make_float4(1.f, 1.f, 1.f, 1.f);
+        uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
+        uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
+        float4 ut4, up4, ur4;
+        const float qnan = __int_as_float(0x7fc00000);
+        if (i + 3 < n) {
+            x = pcl_ld4(s.x + i), y = pcl_ld4(s.y + i), z = pcl_ld4(s.z + i);
+            vx = pcl_ld4(s.vx + i), vy = pcl_ld4(s.vy + i), vz = pcl_ld4(s.vz + i);
+            if (WAVE) e = pcl_ld4(s.e + i);
+            if (has_id) id = pcl_ld4u(s.id + i);
+            if (s.nscat) nsc = pcl_ld4u(s.nscat + i);
+            if (INJ) {
+                ut4 = pcl_ld4(K.u_theta + i);
+                up4 = pcl_ld4(K.u_phi + i);
+                ur4 = pcl_ld4(K.u_rand + i);
+            }
+        } else {  // last, partial group (or past the end): guarded scalar loads, missing slots are "retired"
+            x = make_float4(qnan, qnan, qnan, qnan);
+            y = z = vx = vy = vz = make_float4(0.f, 0.f, 0.f, 0.f);
+            ut4 = up4 = ur4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                if (i + l < n) {
+                    pcl_f4(x, l) = s.x[i + l];
+                    pcl_f4(y, l) = s.y[i + l];
+                    pcl_f4(z, l) = s.z[i + l];
+                    pcl_f4(vx, l) = s.vx[i + l];
+                    pcl_f4(vy, l) = s.vy[i + l];
+                    pcl_f4(vz, l) = s.vz[i + l];
+                    if (WAVE) pcl_f4(e, l) = s.e[i + l];
+                    if (has_id) pcl_u4(id, l) = s.id[i + l];
+                    if (s.nscat) pcl_u4(nsc, l) = s.nscat[i + l];
+                    if (INJ) {
+                        pcl_f4(ut4, l) = K.u_theta[i + l];
+                        pcl_f4(up4, l) = K.u_phi[i + l];
+                        pcl_f4(ur4, l) = K.u_rand[i + l];
+                    }
+                }
+            }
+        }
+        uint32_t keep = 0u;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (pcl_f4(x, l) != pcl_f4(x, l)) continue;
             float ut, up, ur;
             if (INJ) {
-                ut = K.u_theta[i];
-                up = K.u_phi[i];
-                ur = K.u_rand[i];
+                ut = pcl_f4(ut4, l);
+                up = pcl_f4(up4, l);
+                ur = pcl_f4(ur4, l);
             } else {
-                uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-                pcl_draw(K, gid, ut, up, ur);
+                pcl_draw(K, s.id_base + (uint64_t)pcl_u4(id, l), ut, up, ur);
             }
-            float e = WAVE ? p.e[i] : 1.f;
-            uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz);
-            if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
-                float r2 = xx * xx;
-                r2 = fmaf(yy, yy, r2);
-                r2 = fmaf(zz, zz, r2);
-                if (r2 >= K.r2_escape) f |= F_ESCAPED;
+            uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                   pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut, up, ur, cnt);
+            if (!DEL && (f & F_SCATTERED)) pcl_u4(nsc, l) += 1u;
+            if (!(f & (F_ABSORBED | F_ESCAPED))) keep |= 1u << l;
+        }
+        // exclusive rank of this thread's first survivor inside the tile
+        const uint32_t c = __popc(keep);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < PCL_WARPS; ++w) {
+                uint32_t t = s_warp[w];
+                s_warp[w] = tot;
+                tot += t;
             }
-            cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
-            cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
-            cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
-            if (f & (F_ABSORBED | F_ESCAPED)) {
-                xx = qnan;
-            } else {
-                pcl_tally_one(K, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
-            }
-            p.x[i] = xx;
-            p.y[i] = yy;
-            p.z[i] = zz;
-            if (!DEL && (f & F_SCATTERED)) {
-                p.vx[i] = vx;
-                p.vy[i] = vy;
-                p.vz[i] = vz;
-                if (p.nscat) p.nscat[i] += 1u;
-            }
+            s_base = tot ? atomicAdd(n_out, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        uint64_t o = s_base + s_warp[wid] + (inc - c);
+        __syncthreads();  // s_warp / s_base are rewritten by the next tile
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (!(keep & (1u << l))) continue;
+            d.x[o] = pcl_f4(x, l);
+            d.y[o] = pcl_f4(y, l);
+            d.z[o] = pcl_f4(z, l);
+            d.vx[o] = pcl_f4(vx, l);
+            d.vy[o] = pcl_f4(vy, l);
+            d.vz[o] = pcl_f4(vz, l);
+            if (WAVE) d.e[o] = pcl_f4(e, l);
+            d.id[o] = pcl_u4(id, l);
+            if (s.nscat) d.nscat[o] = pcl_u4(nsc, l);
+            ++o;
         }
     }
     pcl_flush_tally(cnt, row, K.nplanes);
@@ -403,44 +523,57 @@ static int fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params
 }
 
 template <bool WAVE, bool DEL, bool INJ, bool PL>
-static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const StepK &K, int64_t *row) {
-    bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) && pcl_aligned16(p.vx) &&
-                   pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
-                   pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
-                   pcl_aligned16(K.u_rand);
-    uint64_t nvec = aligned ? p.n / 4 : 0;
+static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
+                            int64_t *row, uint64_t *n_out) {
+    const bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) && pcl_aligned16(p.vx) &&
+                         pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
+                         pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
+                         pcl_aligned16(K.u_rand);
+    if (dst) {  // retire-and-compact form: one kernel handles every slot, tail included
+        PCL_REQUIRE(ctx, aligned, "the compacting step needs 16-byte aligned planes");
+        PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
+        unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
+        pcl_k_photon_step_compact<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, *dst, K, row,
+                                                                                     (unsigned long long *)n_out);
+        PCL_LAUNCHED(ctx);
+        return 0;
+    }
+    const uint64_t nvec = aligned ? p.n / 4 : 0;
     if (nvec) {
         unsigned grid = pcl_stream_grid(ctx, nvec, PCL_BLOCK, 8);
-        pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, nvec);
+        pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row);
         PCL_LAUNCHED(ctx);
     }
-    uint64_t begin = nvec * 4;
-    if (begin < p.n) {
-        unsigned grid = (unsigned)((p.n - begin + PCL_BLOCK - 1) / PCL_BLOCK);
-        pcl_k_photon_step_tail<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, begin, p.n);
+    // scalar kernel: everything when unaligned, else the (< 4 slot) tail; with a device-side count the
+    // tail position is only known on the device, so the one-block launch is unconditional
+    if (!aligned || p.n_dev || (p.n & 3)) {
+        const uint64_t work = aligned ? 4 : p.n;
+        unsigned grid = pcl_stream_grid(ctx, work, PCL_BLOCK, 8);
+        pcl_k_photon_step_tail<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, aligned ? 1 : 0);
         PCL_LAUNCHED(ctx);
     }
     return 0;
 }
 
 template <bool WAVE, bool DEL, bool INJ>
-static int launch_photon(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const StepK &K, int64_t *row) {
-    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, K, row)
-                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, K, row);
+static int launch_photon(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
+                         int64_t *row, uint64_t *n_out) {
+    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, dst, K, row, n_out)
+                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, dst, K, row, n_out);
 }
 
-static int photon_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const StepK &K, uint32_t mode,
-                           int64_t *row) {
+static int photon_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, const StepK &K,
+                           uint32_t mode, int64_t *row, uint64_t *n_out) {
     const bool wave = mode & PCL_SCATTER_WAVELENGTH, del = mode & PCL_SCATTER_DELETE, inj = K.u_rand != nullptr;
     switch ((wave ? 4 : 0) | (del ? 2 : 0) | (inj ? 1 : 0)) {
-        case 0: return launch_photon<false, false, false>(ctx, st, *p, K, row);
-        case 1: return launch_photon<false, false, true>(ctx, st, *p, K, row);
-        case 2: return launch_photon<false, true, false>(ctx, st, *p, K, row);
-        case 3: return launch_photon<false, true, true>(ctx, st, *p, K, row);
-        case 4: return launch_photon<true, false, false>(ctx, st, *p, K, row);
-        case 5: return launch_photon<true, false, true>(ctx, st, *p, K, row);
-        case 6: return launch_photon<true, true, false>(ctx, st, *p, K, row);
-        default: return launch_photon<true, true, true>(ctx, st, *p, K, row);
+        case 0: return launch_photon<false, false, false>(ctx, st, *p, dst, K, row, n_out);
+        case 1: return launch_photon<false, false, true>(ctx, st, *p, dst, K, row, n_out);
+        case 2: return launch_photon<false, true, false>(ctx, st, *p, dst, K, row, n_out);
+        case 3: return launch_photon<false, true, true>(ctx, st, *p, dst, K, row, n_out);
+        case 4: return launch_photon<true, false, false>(ctx, st, *p, dst, K, row, n_out);
+        case 5: return launch_photon<true, false, true>(ctx, st, *p, dst, K, row, n_out);
+        case 6: return launch_photon<true, true, false>(ctx, st, *p, dst, K, row, n_out);
+        default: return launch_photon<true, true, true>(ctx, st, *p, dst, K, row, n_out);
     }
 }
 
@@ -452,23 +585,81 @@ static int check_photon_view(pcl_ctx *ctx, const pcl_soa *p, const pcl_scatter_p
     return 0;
 }
 
-int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, const pcl_scatter_params *sp,
-                         const pcl_rng *rng, float escape_r2, const pcl_planes *planes, int64_t *tally_row) {
+int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
+                         const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                         int64_t *tally_row, uint64_t *n_out) {
     int rc = check_photon_view(ctx, p, sp);
     if (rc) return rc;
     PCL_REQUIRE(ctx, tally_row != nullptr, "tally_row is required");
+    if (dst) {
+        PCL_REQUIRE(ctx, n_out != nullptr, "n_out_dev is required");
+        PCL_REQUIRE(ctx, dst->x && dst->y && dst->z && dst->vx && dst->vy && dst->vz && dst->id,
+                    "dst needs r, v and id planes");
+        PCL_REQUIRE(ctx, dst->x != p->x, "the compacting step writes out of place");
+        if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, dst->e != nullptr, "dst needs the e plane");
+        if (p->nscat) PCL_REQUIRE(ctx, dst->nscat != nullptr, "dst needs the nscat plane");
+        if (p->n == 0) {
+            PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
+            return 0;
+        }
+    }
     if (p->n == 0) return 0;
     StepK K;
     rc = fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
     if (rc) return rc;
-    return photon_dispatch(ctx, st, p, K, sp->mode, tally_row);
+    return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out);
 }
 
 extern "C" int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                                const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                                const pcl_planes *planes, int64_t *tally_row) {
     PCL_ENTER(ctx);
-    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, dt, sp, rng, escape_r2, planes, tally_row);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, nullptr, dt, sp, rng, escape_r2, planes, tally_row, nullptr);
+}
+
+extern "C" int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_soa *dst, float dt,
+                                       const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                                       const pcl_planes *planes, int64_t *tally_row, uint64_t *n_out_dev) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, dst != nullptr, "dst is required");
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, src, dst, dt, sp, rng, escape_r2, planes, tally_row, n_out_dev);
+}
+
+extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float dt,
+                                   const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                                   const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps,
+                                   uint32_t compact_every) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, pp != nullptr && rng != nullptr && tally_table != nullptr, "null argument");
+    PCL_REQUIRE(ctx, rng->u_rand == nullptr, "multi-step runs draw from Philox; injected uniforms are per step");
+    PCL_REQUIRE(ctx, pp->cur < 2 && pp->n_dev != nullptr, "bad ping-pong state");
+    cudaStream_t st = (cudaStream_t)stream;
+    PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
+    pcl_rng r = *rng;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        r.step = rng->step + s;
+        int64_t *row = tally_table + (size_t)s * PCL_TALLY_COLS;
+        pcl_soa src = pp->buf[pp->cur];
+        src.n_dev = pp->n_dev + pp->cur;
+        if (!((pp->id_valid >> pp->cur) & 1u)) src.id = nullptr;
+        const bool compacting = compact_every && ((uint64_t)r.step + 1) % compact_every == 0;
+        int rc;
+        if (compacting) {
+            pcl_soa dst = pp->buf[pp->cur ^ 1];
+            dst.n = src.n;
+            rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, &r, escape_r2, planes, row, pp->n_dev + (pp->cur ^ 1));
+            if (rc == 0) {
+                pp->buf[pp->cur ^ 1].n = src.n;  // upper bound; the exact count is n_dev[cur]
+                pp->buf[pp->cur ^ 1].id_base = src.id_base;
+                pp->cur ^= 1;
+                pp->id_valid |= 1u << pp->cur;
+            }
+        } else {
+            rc = pcl_photon_step_impl(ctx, st, &src, nullptr, dt, sp, &r, escape_r2, planes, row, nullptr);
+        }
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
@@ -483,8 +674,8 @@ extern "C" int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p
     pcl_rng r = *rng;
     for (uint32_t s = 0; s < nsteps; ++s) {
         r.step = rng->step + s;
-        int rc = pcl_photon_step_impl(ctx, st, p, dt, sp, &r, escape_r2, planes,
-                                      tally_table + (size_t)s * PCL_TALLY_COLS);
+        int rc = pcl_photon_step_impl(ctx, st, p, nullptr, dt, sp, &r, escape_r2, planes,
+                                      tally_table + (size_t)s * PCL_TALLY_COLS, nullptr);
         if (rc) return rc;
     }
     return 0;
@@ -496,6 +687,7 @@ extern "C" int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, con
     int rc = check_photon_view(ctx, p, sp);
     if (rc) return rc;
     PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "stand-alone scatter reads the dr planes");
+    PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     StepK K;
     rc = fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr);
@@ -523,6 +715,7 @@ extern "C" int pcl_escape(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, floa
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, p != nullptr && p->x && p->y && p->z, "r planes are required");
     PCL_REQUIRE(ctx, r2 > 0.f, "escape radius must be positive");
+    PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
     pcl_k_escape<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(*p, r2, tally_row, p->n);
@@ -536,6 +729,7 @@ extern "C" int pcl_tally(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const
     PCL_REQUIRE(ctx, p != nullptr && tally_row != nullptr, "null argument");
     PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
     if (planes && planes->count) PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "plane tallies read the dr planes");
+    PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     StepK K;
     int rc = fill_stepk(ctx, K, 0.f, nullptr, nullptr, 0.f, planes);

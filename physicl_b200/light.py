@@ -315,10 +315,10 @@ class _DeviceMeasureStep(physicl.MeasureStep):
         self._data = v
         self._pending = []
 
-    def _note_row(self, sim, row):
+    def _note_row(self, sim, row, t=None):
         if hasattr(row, "plane_slice") and hasattr(self, "_plane0"):
             self._plane0 = row.plane_slice[0]
-        self._pending.append((sim.t, sim.store, int(row), bool(sim.shard)))
+        self._pending.append((sim.t if t is None else t, sim.store, int(row), bool(sim.shard)))
 
     def _planes(self):
         return []

@@ -217,3 +217,36 @@ def test_device_info_and_launch_accounting():
     assert ctx.fp32_peak_tflops() > 20 and ctx.copy_peak_gbs(1 << 28) > 2000
     assert ctx.launches > 0
     ctx.close()
+
+
+def test_bulk_run_steps_equals_threaded_run():
+    """Simulation.run_steps (k timesteps per C-ABI call) and the threaded per-step loop give the
+    same rows and the same particles."""
+    a, esc_a, sign_a, plane_a = _pipeline(True, n=30000, steps=40, seed=12)
+    x = phys.Simulation(cl_on=True, fuse=True, seed=12)
+    n = 30000
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x.add_particles(r, v, E=np.ones(n))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(0.001), n=np.double(0.001)))
+    esc = phys.light.EscapeSphereStep(1.0e6)
+    x.add_step(3, esc)
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    plane = phys.light.ScatterMeasureStep(None, True, [[2.0e5, np.nan, np.nan], [np.nan, np.nan, 0.0]])
+    x.add_step(4, sign)
+    x.add_step(5, plane)
+    x.run_steps(25)
+    x.run_steps(15)
+    assert len(x.ts) == 40 and x.step_index == 40
+    sa, sb = np.array(sign_a.data), np.array(sign.data)
+    assert np.array_equal(sa[:, 1:], sb[:, 1:]) and np.allclose(sa[:, 0], sb[:, 0], rtol=1e-12)
+    assert np.array_equal(np.array(plane_a.data)[:, 1:], np.array(plane.data)[:, 1:])
+    assert np.array_equal(esc_a.escaped, esc.escaped)
+    pa, pb = a.store.snapshot("photon"), x.store.snapshot("photon")
+    assert np.array_equal(pa["id"], pb["id"])
+    for nm in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(pa[nm].view(np.uint32), pb[nm].view(np.uint32)), nm
+    assert x.cl_ctx.launches <= a.cl_ctx.launches

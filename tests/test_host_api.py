@@ -265,7 +265,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_capi.Soa) == 8 + 15 * 8 + 8
+    assert ctypes.sizeof(_capi.Soa) == 8 + 15 * 8 + 8 + 8
+    assert ctypes.sizeof(_capi.Pingpong) == 2 * ctypes.sizeof(_capi.Soa) + 8 + 4 + 4
     assert ctypes.sizeof(_capi.ScatterParams) == 16
     assert ctypes.sizeof(_capi.Rng) == 8 + 4 + 4 + 3 * 8
     assert ctypes.sizeof(_capi.Planes) == 4 + 4 * 8 + 4 * 8
