@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphysicl_b200.so")
+# PHYSICL_B200_LIB: kernel-tuning aid, points at an alternative build of the same sources
+LIB_PATH = os.environ.get("PHYSICL_B200_LIB") or os.path.join(_HERE, "libphysicl_b200.so")
 
 MAX_PLANES = 8
 TALLY_COLS = 16

@@ -11,7 +11,13 @@
 
 #include "../../include/physicl_b200.h"
 
+#ifndef PCL_BLOCK
 #define PCL_BLOCK 256
+#endif
+// minimum resident CTAs per SM requested from ptxas for the fused photon kernels (register cap)
+#ifndef PCL_PHOTON_MINB
+#define PCL_PHOTON_MINB 4
+#endif
 #define PCL_WARPS (PCL_BLOCK / 32)
 
 struct pcl_graph_key {

@@ -168,7 +168,7 @@ __device__ __forceinline__ uint64_t pcl_valid_slots(const pcl_soa &p) {
 // Fused photon step, in place, 4 photons per thread.
 // ---------------------------------------------------------------------------------------------
 template <bool WAVE, bool DEL, bool INJ, bool PL>
-__global__ void __launch_bounds__(PCL_BLOCK)
+__global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
 pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     uint32_t cnt[NC];
@@ -223,10 +223,40 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
             if (p.nscat) pcl_st4u(p.nscat + i, nsc);
         }
     }
+    // the (< 4 slot) tail, scalar, by the first lanes of block 0
+    {
+        const uint64_t end = pcl_valid_slots(p);
+        const uint64_t i = nvec * 4 + threadIdx.x;
+        if (blockIdx.x == 0 && i < end) {
+            float x = p.x[i];
+            if (x == x) {
+                float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+                float ut, up, ur;
+                if (INJ) {
+                    ut = K.u_theta[i];
+                    up = K.u_phi[i];
+                    ur = K.u_rand[i];
+                } else {
+                    uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
+                    pcl_draw(K, gid, ut, up, ur);
+                }
+                uint32_t f = pcl_photon_one<WAVE, DEL>(K, x, y, z, vx, vy, vz, WAVE ? p.e[i] : 1.f, ut, up, ur, cnt);
+                p.x[i] = x;
+                p.y[i] = y;
+                p.z[i] = z;
+                if (!DEL && (f & F_SCATTERED)) {
+                    p.vx[i] = vx;
+                    p.vy[i] = vy;
+                    p.vz[i] = vz;
+                    if (p.nscat) p.nscat[i] += 1u;
+                }
+            }
+        }
+    }
     pcl_flush_tally(cnt, row, K.nplanes);
 }
 
-// scalar form: the n % 4 tail, and views that are not 16-byte aligned
+// scalar form for views that are not 16-byte aligned
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
@@ -273,9 +303,11 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 // Traffic per live photon-step: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
 // ---------------------------------------------------------------------------------------------
 template <bool WAVE, bool DEL, bool INJ, bool PL>
-__global__ void __launch_bounds__(PCL_BLOCK)
+__global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
 pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned long long *n_out) {
     constexpr int NC = PL ? C_N : C_PLANE0;
+    constexpr int NST = WAVE ? 9 : 8;  // staged planes: x y z vx vy vz id nscat [e]
+    __shared__ float s_stage[NST][PCL_BLOCK * 4];
     __shared__ uint32_t s_warp[PCL_WARPS];
     __shared__ unsigned long long s_base;
     uint32_t cnt[NC];
@@ -344,7 +376,8 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
             if (!DEL && (f & F_SCATTERED)) pcl_u4(nsc, l) += 1u;
             if (!(f & (F_ABSORBED | F_ESCAPED))) keep |= 1u << l;
         }
-        // exclusive rank of this thread's first survivor inside the tile
+        // tile-local rank of this thread's first survivor: shuffle scan inside the warp, warp totals
+        // through shared memory
         const uint32_t c = __popc(keep);
         uint32_t inc = c;
 #pragma unroll
@@ -354,33 +387,46 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
         }
         if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
+        uint32_t wbase = 0, tot = 0;
 #pragma unroll
-            for (int w = 0; w < PCL_WARPS; ++w) {
-                uint32_t t = s_warp[w];
-                s_warp[w] = tot;
-                tot += t;
-            }
-            s_base = tot ? atomicAdd(n_out, (unsigned long long)tot) : 0ull;
+        for (int w = 0; w < PCL_WARPS; ++w) {
+            uint32_t t = s_warp[w];
+            wbase += (w < (int)wid) ? t : 0u;
+            tot += t;
         }
-        __syncthreads();
-        uint64_t o = s_base + s_warp[wid] + (inc - c);
-        __syncthreads();  // s_warp / s_base are rewritten by the next tile
+        if (threadIdx.x == 0) s_base = tot ? atomicAdd(n_out, (unsigned long long)tot) : 0ull;
+        // stage the survivors, plane by plane, at their tile-local rank
+        uint32_t rk = wbase + (inc - c);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             if (!(keep & (1u << l))) continue;
-            d.x[o] = pcl_f4(x, l);
-            d.y[o] = pcl_f4(y, l);
-            d.z[o] = pcl_f4(z, l);
-            d.vx[o] = pcl_f4(vx, l);
-            d.vy[o] = pcl_f4(vy, l);
-            d.vz[o] = pcl_f4(vz, l);
-            if (WAVE) d.e[o] = pcl_f4(e, l);
-            d.id[o] = pcl_u4(id, l);
-            if (s.nscat) d.nscat[o] = pcl_u4(nsc, l);
-            ++o;
+            s_stage[0][rk] = pcl_f4(x, l);
+            s_stage[1][rk] = pcl_f4(y, l);
+            s_stage[2][rk] = pcl_f4(z, l);
+            s_stage[3][rk] = pcl_f4(vx, l);
+            s_stage[4][rk] = pcl_f4(vy, l);
+            s_stage[5][rk] = pcl_f4(vz, l);
+            s_stage[6][rk] = __uint_as_float(pcl_u4(id, l));
+            s_stage[7][rk] = __uint_as_float(pcl_u4(nsc, l));
+            if (WAVE) s_stage[NST - 1][rk] = pcl_f4(e, l);
+            ++rk;
         }
+        __syncthreads();
+        // coalesced copy-out: consecutive threads write consecutive survivors
+        const unsigned long long base = s_base;
+        for (uint32_t q = threadIdx.x; q < tot; q += PCL_BLOCK) {
+            const unsigned long long o = base + q;
+            d.x[o] = s_stage[0][q];
+            d.y[o] = s_stage[1][q];
+            d.z[o] = s_stage[2][q];
+            d.vx[o] = s_stage[3][q];
+            d.vy[o] = s_stage[4][q];
+            d.vz[o] = s_stage[5][q];
+            d.id[o] = __float_as_uint(s_stage[6][q]);
+            if (s.nscat) d.nscat[o] = __float_as_uint(s_stage[7][q]);
+            if (WAVE) d.e[o] = s_stage[NST - 1][q];
+        }
+        __syncthreads();  // the stage and s_warp are rewritten by the next tile
     }
     pcl_flush_tally(cnt, row, K.nplanes);
 }
@@ -538,18 +584,14 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         PCL_LAUNCHED(ctx);
         return 0;
     }
-    const uint64_t nvec = aligned ? p.n / 4 : 0;
-    if (nvec) {
-        unsigned grid = pcl_stream_grid(ctx, nvec, PCL_BLOCK, 8);
+    if (aligned) {
+        unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
         pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row);
         PCL_LAUNCHED(ctx);
     }
-    // scalar kernel: everything when unaligned, else the (< 4 slot) tail; with a device-side count the
-    // tail position is only known on the device, so the one-block launch is unconditional
-    if (!aligned || p.n_dev || (p.n & 3)) {
-        const uint64_t work = aligned ? 4 : p.n;
-        unsigned grid = pcl_stream_grid(ctx, work, PCL_BLOCK, 8);
-        pcl_k_photon_step_tail<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, aligned ? 1 : 0);
+    if (!aligned) {  // scalar kernel for views that cannot take 128-bit accesses
+        unsigned grid = pcl_stream_grid(ctx, p.n, PCL_BLOCK, 8);
+        pcl_k_photon_step_tail<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row, 0);
         PCL_LAUNCHED(ctx);
     }
     return 0;

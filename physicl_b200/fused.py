@@ -11,9 +11,11 @@ Retirement policy.  When the pipeline can retire photons (delete scattering, esc
 step runs on the store's ping-pong plane sets through ``pcl_photon_steps_pp``: every m-th timestep is
 a retire-and-compact step, the others update in place.  In-place steps move ~44 B per SLOT, a
 compacting step ~56 B per live photon, so with a death rate d per step the traffic per live
-photon-step is about 44 + 12/m + 22 m d: minimal at m = sqrt(0.545 / d).  d is re-estimated from the
-tallies every ``sim.compact_every`` timesteps (the only host<->device sync in the loop), which also
-refreshes the host's upper bound on the slot count.
+photon-step is about 44 + 12/m + 22 m d: minimal at m = sqrt(0.545 / d).  d comes from the tally
+rows with a lag: after every chunk of ``sim.feedback_every`` timesteps the last row and the device
+slot counters are copied to pinned host memory asynchronously, and the host reads them one or two
+chunks later (it only ever waits on work the GPU has long finished), so the stepping loop has no
+blocking host<->device round trip.
 """
 from __future__ import annotations
 
@@ -42,8 +44,9 @@ class FusedPhotonStep(physicl.Step):
         self._planes = _capi.make_planes(planes)
         self._multi_plane = sum(1 for _, n in self._plane_slices if n) > 1
         self.retires = bool(escape or scatter.mode & _capi.SCATTER_DELETE)
-        self.cadence = 8  # m: every m-th timestep compacts; adapted at sync points
-        self._last_live = None  # (step index, live count) at the previous sync point
+        self.cadence = 4  # m: every m-th timestep compacts; adapted from lagged tally feedback
+        self._fb = []  # pending feedback: (event, pinned int64[18], buffer index at enqueue time)
+        self._fb_pool = []
 
     # ---- helpers --------------------------------------------------------------------------------
     def _fallback(self, st):
@@ -61,19 +64,36 @@ class FusedPhotonStep(physicl.Step):
             for m, sl in zip(self.measures, self._plane_slices):
                 m._note_row(sim, _FusedRow(row, sl), t=None if ts is None else ts[i])
 
-    def _sync_point(self, sim, st, g, last_row, now):
-        """Every sim.compact_every timesteps: read the live count (128-byte D2H), make the slot count
-        exact again and re-derive the compaction cadence from the observed death rate."""
-        live = int(st.peek_row(last_row)[_capi.T_ALIVE])
-        g.n_live = live
-        st.sync_n("photon")
-        if getattr(sim, "compact_cadence", None):
-            self.cadence = int(sim.compact_cadence)
-        elif self._last_live is not None and self._last_live[1] > 0 and now > self._last_live[0]:
-            ratio = max(live, 1) / self._last_live[1]
-            d = 1.0 - ratio ** (1.0 / (now - self._last_live[0]))
-            self.cadence = 64 if d <= 1e-4 else int(min(64, max(1, round(math.sqrt(0.545 / d)))))
-        self._last_live = (now, live)
+    def _enqueue_feedback(self, st, g, last_row):
+        """Async copy of a chunk's last tally row and of the device slot counters to pinned memory."""
+        import torch
+
+        buf = self._fb_pool.pop() if self._fb_pool else torch.empty(18, dtype=torch.int64).pin_memory()
+        buf[:16].copy_(st.tally[last_row - st._row_base], non_blocking=True)
+        buf[16:].copy_(g.n_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(st.device))
+        self._fb.append((ev, buf, g.cur))
+
+    def _consume_feedback(self, sim, g, max_pending=2):
+        """Use whatever feedback has already arrived (never waits unless more than max_pending chunks
+        are outstanding, i.e. the GPU is at least that far behind the host anyway)."""
+        while self._fb and (self._fb[0][0].query() or len(self._fb) > max_pending):
+            ev, buf, cur = self._fb.pop(0)
+            ev.synchronize()
+            row = buf[:16].numpy()
+            live_in, alive = int(row[_capi.T_LIVE_IN]), int(row[_capi.T_ALIVE])
+            died = int(row[_capi.T_ESCAPED]) + int(row[_capi.T_ABSORBED])
+            g.n_live = alive
+            slots = int(buf[16 + cur])
+            if 0 < slots < g.n and not g.n_exact:
+                g.n = slots  # slot counts only shrink: a stale exact count is still an upper bound
+            if getattr(sim, "compact_cadence", None):
+                self.cadence = int(sim.compact_cadence)
+            elif live_in > 0:
+                d = died / live_in
+                self.cadence = 64 if d <= 1e-4 else int(min(64, max(1, round(math.sqrt(0.545 / d)))))
+            self._fb_pool.append(buf)
 
     # ---- k timesteps with one C-ABI call ----------------------------------------------------------
     def run_many(self, sim, k, dt, ts):
@@ -93,6 +113,7 @@ class FusedPhotonStep(physicl.Step):
         for nm in ("dx", "dy", "dz"):  # dr stays in registers; stale planes would mislead host readers
             g.planes.pop(nm, None)
         if self.retires:
+            self._consume_feedback(sim, g)
             if getattr(sim, "compact_cadence", None):
                 self.cadence = int(sim.compact_cadence)
             pp = st.pingpong("photon")
@@ -112,8 +133,8 @@ class FusedPhotonStep(physicl.Step):
         self._note(sim, first, k, ts)
         last = first + k - 1
         sim._mark_device_dirty(live_row=last)
-        if self.retires and sim.compact_every and (sim.step_index + k) % sim.compact_every == 0:
-            self._sync_point(sim, st, g, last, sim.step_index + k)
+        if self.retires and sim.feedback_every and (sim.step_index + k) % sim.feedback_every == 0:
+            self._enqueue_feedback(st, g, last)
 
     # ---- one timestep --------------------------------------------------------------------------------
     def run(self, sim):

@@ -12,7 +12,7 @@ from physicl_b200 import _capi
 
 n = bench.PHOTONS_PER_GPU
 sim, esc, sign = bench.photon_sim(n, 0, 0)
-sim.compact_every = 0
+sim.feedback_every = 0
 sim.run_steps(3)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
