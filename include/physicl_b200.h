@@ -215,6 +215,7 @@ int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
 /* ---- roofline denominators measured on the box --------------------------------------------- */
 /* FFMA-only and copy micro-kernels; results in TFLOP/s (2 flop per FMA) and GB/s (read+write). */
 int pcl_measure_fp32_peak(pcl_ctx *ctx, double *tflops);
+int pcl_measure_fp32x2_peak(pcl_ctx *ctx, double *tflops); /* packed FFMA2 (fma.rn.f32x2) rate */
 int pcl_measure_copy_peak(pcl_ctx *ctx, uint64_t bytes, double *gbs);
 
 #ifdef __cplusplus

@@ -86,6 +86,7 @@ _PROTOS = {
     "pcl_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pcl_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pcl_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "pcl_measure_fp32x2_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pcl_measure_copy_peak": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
 }
 EXPORTS = tuple(_PROTOS)
@@ -153,6 +154,11 @@ class Context:
     def fp32_peak_tflops(self) -> float:
         v = C.c_double()
         self.call("pcl_measure_fp32_peak", C.byref(v))
+        return v.value
+
+    def fp32x2_peak_tflops(self) -> float:
+        v = C.c_double()
+        self.call("pcl_measure_fp32x2_peak", C.byref(v))
         return v.value
 
     def copy_peak_gbs(self, nbytes: int = 1 << 30) -> float:

@@ -103,6 +103,130 @@ pcl_k_gravity(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed-FP32 form (Blackwell FFMA2 / FADD2 / FMUL2 = PTX fma/add/sub/mul.rn.f32x2).  The scalar
+// kernel above is limited by issue slots (13.9 warp instructions per interaction, of which 12 FP32);
+// here one instruction carries the same operation for TWO j-bodies, so an interaction costs
+// 6 packed FP32 + 1 MUFU + 0.5 LDS issue slots and the FMA pipe, not the scheduler, is the limit.
+// j-bodies are staged in shared memory as pairs: A = (x0,x1,y0,y1), B = (z0,z1,m0,m1), so a pair
+// arrives as two LDS.128 whose register halves already are the packed operands.
+// Rounding is IEEE per element (identical to the scalar fmaf/add/mul); only the summation order of
+// the j contributions differs from the scalar kernel.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+template <int IB, int T, int JT>
+__global__ void __launch_bounds__(T)
+pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__restrict__ pj, uint64_t n_total,
+                 float G, float eps2, float *ax, float *ay, float *az, int accumulate) {
+    constexpr int NP = JT / 2;            // j pairs per tile
+    constexpr int LP = (NP + T - 1) / T;  // pairs loaded per thread per tile
+    __shared__ ulonglong2 s_a[2][NP];     // (x0,x1), (y0,y1)
+    __shared__ ulonglong2 s_b[2][NP];     // (z0,z1), (m0,m1)
+    const uint64_t i0 = (uint64_t)blockIdx.x * (T * IB) + threadIdx.x;
+    f32x2 xi[IB], yi[IB], zi[IB], axi[IB], ayi[IB], azi[IB];
+#pragma unroll
+    for (int m = 0; m < IB; ++m) {
+        uint64_t i = i0 + (uint64_t)m * T;
+        float4 b = (i < n_local) ? pi[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xi[m] = pk(b.x, b.x);
+        yi[m] = pk(b.y, b.y);
+        zi[m] = pk(b.z, b.z);
+        axi[m] = ayi[m] = azi[m] = pk(0.f, 0.f);
+    }
+    const f32x2 eps = pk(eps2, eps2);
+    const uint64_t ntile = (n_total + JT - 1) / JT;
+    float4 r0[LP], r1[LP];  // next tile, register staged
+    auto fetch = [&](uint64_t t) {
+#pragma unroll
+        for (int u = 0; u < LP; ++u) {
+            const int q = threadIdx.x + u * T;
+            const uint64_t j = t * JT + 2 * (uint64_t)q;
+            r0[u] = (q < NP && j < n_total) ? pj[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[u] = (q < NP && j + 1 < n_total) ? pj[j + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < LP; ++u) {
+            const int q = threadIdx.x + u * T;
+            if (q < NP) {
+                s_a[buf][q] = make_ulonglong2(pk(r0[u].x, r1[u].x), pk(r0[u].y, r1[u].y));
+                s_b[buf][q] = make_ulonglong2(pk(r0[u].z, r1[u].z), pk(r0[u].w, r1[u].w));
+            }
+        }
+    };
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    for (uint64_t t = 0; t < ntile; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < ntile) fetch(t + 1);  // global loads in flight while this tile is consumed
+#pragma unroll 4
+        for (int q = 0; q < NP; ++q) {
+            const ulonglong2 A = s_a[buf][q], B = s_b[buf][q];
+#pragma unroll
+            for (int m = 0; m < IB; ++m) {
+                f32x2 dx = sub2(A.x, xi[m]), dy = sub2(A.y, yi[m]), dz = sub2(B.x, zi[m]);
+                f32x2 r2 = fma2(dx, dx, eps);
+                r2 = fma2(dy, dy, r2);
+                r2 = fma2(dz, dz, r2);
+                float lo, hi;
+                upk(r2, lo, hi);
+                f32x2 rinv = pk(pcl_rsqrt_approx(lo), pcl_rsqrt_approx(hi));
+                f32x2 rinv2 = mul2(rinv, rinv);
+                f32x2 sc = mul2(B.y, rinv);
+                sc = mul2(sc, rinv2);
+                axi[m] = fma2(sc, dx, axi[m]);
+                ayi[m] = fma2(sc, dy, ayi[m]);
+                azi[m] = fma2(sc, dz, azi[m]);
+            }
+        }
+        if (t + 1 < ntile) stage(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < IB; ++m) {
+        uint64_t i = i0 + (uint64_t)m * T;
+        if (i < n_local) {
+            float a0, a1, b0, b1, c0, c1;
+            upk(axi[m], a0, a1);
+            upk(ayi[m], b0, b1);
+            upk(azi[m], c0, c1);
+            float gx = G * (a0 + a1), gy = G * (b0 + b1), gz = G * (c0 + c1);
+            if (accumulate) {
+                gx += ax[i];
+                gy += ay[i];
+                gz += az[i];
+            }
+            ax[i] = gx;
+            ay[i] = gy;
+            az[i] = gz;
+        }
+    }
+}
+
 extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
                                  const float *posm_all, uint64_t n_total, float G, float eps2, float *ax, float *ay,
                                  float *az, int accumulate) {
@@ -123,6 +247,9 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
 #define PCL_GRAV(IB, T)                                                                                       \
     pcl_k_gravity<IB, T><<<(unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), T, 0, st>>>(                  \
         (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
+#define PCL_GRAV2(IB, T, JT)                                                                                  \
+    pcl_k_gravity_x2<IB, T, JT><<<(unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), T, 0, st>>>(           \
+        (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
     switch (variant) {
         case 1: PCL_GRAV(4, 128); break;
         case 2: PCL_GRAV(2, 128); break;
@@ -130,9 +257,17 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
         case 4: PCL_GRAV(8, 64); break;
         case 5: PCL_GRAV(8, 32); break;
         case 6: PCL_GRAV(4, 32); break;
-        default: PCL_GRAV(4, 64); break;
+        case 7: PCL_GRAV(4, 64); break;
+        case 10: PCL_GRAV2(2, 128, 256); break;
+        case 11: PCL_GRAV2(4, 64, 256); break;
+        case 12: PCL_GRAV2(1, 256, 512); break;
+        case 13: PCL_GRAV2(2, 128, 1024); break;
+        case 14: PCL_GRAV2(2, 64, 256); break;
+        case 15: PCL_GRAV2(1, 128, 256); break;
+        default: PCL_GRAV2(2, 128, 512); break;
     }
 #undef PCL_GRAV
+#undef PCL_GRAV2
     PCL_LAUNCHED(ctx);
     return 0;
 }

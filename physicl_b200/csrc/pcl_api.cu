@@ -123,6 +123,55 @@ __global__ void __launch_bounds__(256) pcl_k_ffma_peak(float *out, int iters, fl
     if (s == 123.456f) out[0] = s;  // keep the loop alive
 }
 
+__global__ void __launch_bounds__(256) pcl_k_ffma2_peak(float *out, int iters, float a, float b) {
+    unsigned long long r[8], pa, pb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = (float)(threadIdx.x + i) * 1e-3f;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(r[i]) : "f"(v));
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(pa), "l"(pb));
+    }
+    unsigned long long x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x ^= r[i];
+    if (x == 0x123456789abcdefull) out[0] = 1.f;
+}
+
+// packed (FFMA2) rate: same units as pcl_measure_fp32_peak (2 flop per FMA lane-element)
+extern "C" int pcl_measure_fp32x2_peak(pcl_ctx *ctx, double *tflops) {
+    PCL_ENTER(ctx);
+    float *d = nullptr;
+    PCL_CUDA(ctx, cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    PCL_CUDA(ctx, cudaEventCreate(&e0));
+    PCL_CUDA(ctx, cudaEventCreate(&e1));
+    const int iters = 4096;
+    const int blocks = ctx->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        PCL_CUDA(ctx, cudaEventRecord(e0, 0));
+        pcl_k_ffma2_peak<<<blocks, 256>>>(d, iters, 0.999f, 1e-4f);
+        PCL_LAUNCHED(ctx);
+        PCL_CUDA(ctx, cudaEventRecord(e1, 0));
+        PCL_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PCL_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (tflops) *tflops = best;
+    return 0;
+}
+
 extern "C" int pcl_measure_fp32_peak(pcl_ctx *ctx, double *tflops) {
     PCL_ENTER(ctx);
     float *d = nullptr;
