@@ -17,6 +17,8 @@
 //
 // Fused step traffic per live photon-step: read r,v 24 B + write r 12 B + write v 12 B for the
 // 16-byte groups that contain a scattered photon (+4 B e, +4 B id, +8 B nscat when present).
+#include <stdlib.h>
+
 #include "pcl_common.cuh"
 
 struct StepK {
@@ -45,8 +47,12 @@ __device__ __forceinline__ float pcl_norm3(float dx, float dy, float dz) {
 }
 
 // The scatter decision and the new direction for one photon.  dx,dy,dz is this step's dr.
+// Written without branches on purpose: every lane evaluates both angles and selects, so the compiler
+// can interleave the four photons a thread owns (independent chains) instead of serialising four
+// divergent bodies.  At warp level nothing is lost: with pcoll ~ 0.3 some lane scatters in
+// practically every warp, so the divergent form executed both sides anyway.
 template <bool WAVE, bool DEL>
-__device__ __forceinline__ uint32_t pcl_scatter_one(float dx, float dy, float dz, float e,
+__device__ __forceinline__ uint32_t pcl_scatter_one(bool live, float dx, float dy, float dz, float e,
                                                     float ut, float up, float ur, float k, float c,
                                                     float &vx, float &vy, float &vz) {
     float norm = pcl_norm3(dx, dy, dz);
@@ -56,16 +62,16 @@ __device__ __forceinline__ uint32_t pcl_scatter_one(float dx, float dy, float dz
         float e4 = e2 * e2;
         pcoll = pcoll * e4;
     }
-    if (!(pcoll >= ur)) return 0u;
-    if (DEL) return F_SCATTERED | F_ABSORBED;
+    const bool hit = live && (pcoll >= ur);
+    if (DEL) return hit ? (F_SCATTERED | F_ABSORBED) : 0u;
     float st, ct, sp, cp;
     pcl_sincospi(ut + ut, st, ct);  // theta = 2*pi*u
     pcl_sincospi(up, sp, cp);       // phi   =   pi*u
     float cs = c * st;
-    vx = cs * cp;
-    vy = cs * sp;
-    vz = c * ct;
-    return F_SCATTERED;
+    vx = hit ? cs * cp : vx;
+    vy = hit ? cs * sp : vy;
+    vz = hit ? c * ct : vz;
+    return hit ? F_SCATTERED : 0u;
 }
 
 __device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut, float &up, float &ur) {
@@ -77,13 +83,13 @@ __device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut
 }
 
 template <int NC>
-__device__ __forceinline__ void pcl_tally_one(const StepK &K, float x, float y, float z, float dx,
+__device__ __forceinline__ void pcl_tally_one(const StepK &K, bool on, float x, float y, float z, float dx,
                                               float dy, float dz, float vx, float vy, float vz,
                                               uint32_t (&cnt)[NC]) {
-    cnt[C_ALIVE] += 1u;
-    cnt[C_XP] += (vx > 0.f) ? 1u : 0u;
-    cnt[C_YP] += (vy > 0.f) ? 1u : 0u;
-    cnt[C_ZP] += (vz > 0.f) ? 1u : 0u;
+    cnt[C_ALIVE] += on ? 1u : 0u;
+    cnt[C_XP] += (on && vx > 0.f) ? 1u : 0u;
+    cnt[C_YP] += (on && vy > 0.f) ? 1u : 0u;
+    cnt[C_ZP] += (on && vz > 0.f) ? 1u : 0u;
 #pragma unroll
     for (int q = 0; q < NC - (int)C_PLANE0; ++q) {
         if ((uint32_t)q < K.nplanes) {
@@ -92,7 +98,7 @@ __device__ __forceinline__ void pcl_tally_one(const StepK &K, float x, float y, 
             float d = ax == 0 ? dx : (ax == 1 ? dy : dz);
             float prev = r - d;  // light.py:386: obj.r[0] - obj.dr[0], evaluated after r += dr
             float loc = K.loc[q];
-            bool hit = (prev <= loc && loc <= r) || (prev >= loc && loc >= r);
+            bool hit = on && ((prev <= loc && loc <= r) || (prev >= loc && loc >= r));
             cnt[C_PLANE0 + q] += hit ? 1u : 0u;
         }
     }
@@ -131,27 +137,24 @@ template <bool WAVE, bool DEL, int NC>
 __device__ __forceinline__ uint32_t pcl_photon_one(const StepK &K, float &x, float &y, float &z, float &vx, float &vy,
                                                    float &vz, float e, float ut, float up, float ur,
                                                    uint32_t (&cnt)[NC]) {
-    cnt[C_LIVEIN] += 1u;
+    const bool live = x == x;  // a retired slot stays retired: NaN + dx is NaN
+    cnt[C_LIVEIN] += live ? 1u : 0u;
     float dx = vx * K.dt, dy = vy * K.dt, dz = vz * K.dt;
     float xx = x + dx, yy = y + dy, zz = z + dz;
-    uint32_t f = pcl_scatter_one<WAVE, DEL>(dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz);
-    if (!(f & F_ABSORBED) && K.r2_escape > 0.f) {
-        float r2 = xx * xx;
-        r2 = fmaf(yy, yy, r2);
-        r2 = fmaf(zz, zz, r2);
-        if (r2 >= K.r2_escape) f |= F_ESCAPED;
-    }
+    uint32_t f = pcl_scatter_one<WAVE, DEL>(live, dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz);
+    float r2 = xx * xx;
+    r2 = fmaf(yy, yy, r2);
+    r2 = fmaf(zz, zz, r2);
+    const bool esc = live && !(f & F_ABSORBED) && K.r2_escape > 0.f && r2 >= K.r2_escape;
+    f |= esc ? F_ESCAPED : 0u;
     cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
     cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
-    cnt[C_ESC] += (f & F_ESCAPED) ? 1u : 0u;
-    if (f & (F_ABSORBED | F_ESCAPED)) {
-        xx = __int_as_float(0x7fc00000);
-    } else {
-        pcl_tally_one(K, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
-    }
-    x = xx;
-    y = yy;
-    z = zz;
+    cnt[C_ESC] += esc ? 1u : 0u;
+    const bool gone = (f & (F_ABSORBED | F_ESCAPED)) != 0u;
+    pcl_tally_one(K, live && !gone, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
+    x = (live && !gone) ? xx : __int_as_float(0x7fc00000);  // retired slots hold the canonical quiet NaN
+    y = live ? yy : y;  // slots retired earlier keep their last position
+    z = live ? zz : z;
     return f;
 }
 
@@ -162,6 +165,74 @@ __device__ __forceinline__ uint64_t pcl_valid_slots(const pcl_soa &p) {
         return nd < p.n ? nd : p.n;
     }
     return p.n;
+}
+
+// Four consecutive photons held in registers: step them and write back in place (r always, v and
+// nscat only when one of the four scattered).  Shared by the register-load and the TMA-staged kernels.
+template <bool WAVE, bool DEL, bool INJ, int NC>
+__device__ __forceinline__ void pcl_step_group4(const pcl_soa &p, const StepK &K, uint64_t i, float4 x, float4 y, float4 z,
+                                                float4 vx, float4 vy, float4 vz, float4 e, uint4 id, bool has_id, uint4 nsc,
+                                                float4 ut4, float4 up4, float4 ur4, uint32_t (&cnt)[NC]) {
+    uint32_t any_scat = 0u;
+    float ut[4], up[4], ur[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {  // four independent Philox chains: the compiler interleaves them
+        if (INJ) {
+            ut[l] = pcl_f4(ut4, l);
+            up[l] = pcl_f4(up4, l);
+            ur[l] = pcl_f4(ur4, l);
+        } else {
+            uint64_t gid = p.id_base + (has_id ? (uint64_t)pcl_u4(id, l) : (i + (uint64_t)l));
+            pcl_draw(K, gid, ut[l], up[l], ur[l]);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l), pcl_f4(vy, l),
+                                               pcl_f4(vz, l), pcl_f4(e, l), ut[l], up[l], ur[l], cnt);
+        const bool sc = !DEL && (f & F_SCATTERED);
+        any_scat |= sc ? 1u : 0u;
+        pcl_u4(nsc, l) += sc ? 1u : 0u;
+    }
+    pcl_st4(p.x + i, x);
+    pcl_st4(p.y + i, y);
+    pcl_st4(p.z + i, z);
+    if (any_scat) {
+        pcl_st4(p.vx + i, vx);
+        pcl_st4(p.vy + i, vy);
+        pcl_st4(p.vz + i, vz);
+        if (p.nscat) pcl_st4u(p.nscat + i, nsc);
+    }
+}
+
+// the (< 4 slot) tail after the last full group, scalar, by the first lanes of block 0
+template <bool WAVE, bool DEL, bool INJ, int NC>
+__device__ __forceinline__ void pcl_step_tail(const pcl_soa &p, const StepK &K, uint64_t first, uint32_t (&cnt)[NC]) {
+    const uint64_t end = pcl_valid_slots(p);
+    const uint64_t i = first + threadIdx.x;
+    if (blockIdx.x != 0 || i >= end) return;
+    float x = p.x[i];
+    if (x != x) return;
+    float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+    float ut, up, ur;
+    if (INJ) {
+        ut = K.u_theta[i];
+        up = K.u_phi[i];
+        ur = K.u_rand[i];
+    } else {
+        uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
+        pcl_draw(K, gid, ut, up, ur);
+    }
+    uint32_t f = pcl_photon_one<WAVE, DEL>(K, x, y, z, vx, vy, vz, WAVE ? p.e[i] : 1.f, ut, up, ur, cnt);
+    p.x[i] = x;
+    p.y[i] = y;
+    p.z[i] = z;
+    if (!DEL && (f & F_SCATTERED)) {
+        p.vx[i] = vx;
+        p.vy[i] = vy;
+        p.vz[i] = vz;
+        if (p.nscat) p.nscat[i] += 1u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -185,73 +256,136 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
         uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
         const bool has_id = p.id != nullptr;
         if (has_id) id = pcl_ld4u(p.id + i);
-        float4 ut4, up4, ur4;
+        float4 ut4 = make_float4(0.f, 0.f, 0.f, 0.f), up4 = ut4, ur4 = ut4;
         if (INJ) {
             ut4 = pcl_ld4(K.u_theta + i);
             up4 = pcl_ld4(K.u_phi + i);
             ur4 = pcl_ld4(K.u_rand + i);
         }
-        uint32_t any_scat = 0u;
         uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
         if (p.nscat) nsc = pcl_ld4u(p.nscat + i);
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            if (pcl_f4(x, l) != pcl_f4(x, l)) continue;  // retired slot
-            float ut, up, ur;
-            if (INJ) {
-                ut = pcl_f4(ut4, l);
-                up = pcl_f4(up4, l);
-                ur = pcl_f4(ur4, l);
-            } else {
-                uint64_t gid = p.id_base + (has_id ? (uint64_t)pcl_u4(id, l) : (i + (uint64_t)l));
-                pcl_draw(K, gid, ut, up, ur);
-            }
-            uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                   pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut, up, ur, cnt);
-            if (!DEL && (f & F_SCATTERED)) {
-                any_scat = 1u;
-                pcl_u4(nsc, l) += 1u;
-            }
-        }
-        pcl_st4(p.x + i, x);
-        pcl_st4(p.y + i, y);
-        pcl_st4(p.z + i, z);
-        if (any_scat) {
-            pcl_st4(p.vx + i, vx);
-            pcl_st4(p.vy + i, vy);
-            pcl_st4(p.vz + i, vz);
-            if (p.nscat) pcl_st4u(p.nscat + i, nsc);
-        }
+        pcl_step_group4<WAVE, DEL, INJ>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, ut4, up4, ur4, cnt);
     }
-    // the (< 4 slot) tail, scalar, by the first lanes of block 0
-    {
-        const uint64_t end = pcl_valid_slots(p);
-        const uint64_t i = nvec * 4 + threadIdx.x;
-        if (blockIdx.x == 0 && i < end) {
-            float x = p.x[i];
-            if (x == x) {
-                float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
-                float ut, up, ur;
-                if (INJ) {
-                    ut = K.u_theta[i];
-                    up = K.u_phi[i];
-                    ur = K.u_rand[i];
-                } else {
-                    uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-                    pcl_draw(K, gid, ut, up, ur);
-                }
-                uint32_t f = pcl_photon_one<WAVE, DEL>(K, x, y, z, vx, vy, vz, WAVE ? p.e[i] : 1.f, ut, up, ur, cnt);
-                p.x[i] = x;
-                p.y[i] = y;
-                p.z[i] = z;
-                if (!DEL && (f & F_SCATTERED)) {
-                    p.vx[i] = vx;
-                    p.vy[i] = vy;
-                    p.vz[i] = vz;
-                    if (p.nscat) p.nscat[i] += 1u;
-                }
-            }
+    pcl_step_tail<WAVE, DEL, INJ>(p, K, nvec * 4, cnt);
+    pcl_flush_tally(cnt, row, K.nplanes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused photon step, in place, with the loads staged through shared memory by the TMA engine.
+// One elected thread issues 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) of the next
+// 1024-slot tile of every plane while the CTA computes the current one from shared memory, so the
+// memory system is kept busy by the copy engine and not by however many warps happen to be waiting.
+// Two stages per CTA (2 x planes x 4 KB).  Stores go straight from registers (STG.128).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pcl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pcl_mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pcl_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pcl_mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pcl_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pcl_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pcl_smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(pcl_smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void pcl_mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCL_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCL_DONE_%=;\n"
+        "bra PCL_WAIT_%=;\n"
+        "PCL_DONE_%=:\n"
+        "}\n" ::"r"(pcl_smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+
+#define PCL_TILE_SLOTS (PCL_BLOCK * 4)
+#define PCL_PLANE_BYTES (PCL_TILE_SLOTS * 4)
+
+template <bool WAVE, bool DEL, bool PL>
+__global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
+pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
+    constexpr int NC = PL ? C_N : C_PLANE0;
+    extern __shared__ __align__(128) unsigned char s_stage_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    uint32_t cnt[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    const bool has_id = p.id != nullptr, has_ns = p.nscat != nullptr;
+    // plane order inside a stage: x y z vx vy vz [e] [id] [nscat]
+    const int q_e = 6, q_id = 6 + (WAVE ? 1 : 0), q_ns = q_id + (has_id ? 1 : 0);
+    const int nplanes = q_ns + (has_ns ? 1 : 0);
+    const uint64_t valid = pcl_valid_slots(p);
+    const uint64_t ntiles = valid / PCL_TILE_SLOTS;
+    if (threadIdx.x == 0) {
+        pcl_mbar_init(&s_bar[0], 1);
+        pcl_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t tile, int st) {  // elected thread only
+        unsigned char *base = s_stage_raw + (size_t)st * nplanes * PCL_PLANE_BYTES;
+        const uint64_t off = tile * PCL_TILE_SLOTS;
+        pcl_mbar_expect_tx(&s_bar[st], (uint32_t)(nplanes * PCL_PLANE_BYTES));
+        pcl_bulk_g2s(base + 0 * PCL_PLANE_BYTES, p.x + off, PCL_PLANE_BYTES, &s_bar[st]);
+        pcl_bulk_g2s(base + 1 * PCL_PLANE_BYTES, p.y + off, PCL_PLANE_BYTES, &s_bar[st]);
+        pcl_bulk_g2s(base + 2 * PCL_PLANE_BYTES, p.z + off, PCL_PLANE_BYTES, &s_bar[st]);
+        pcl_bulk_g2s(base + 3 * PCL_PLANE_BYTES, p.vx + off, PCL_PLANE_BYTES, &s_bar[st]);
+        pcl_bulk_g2s(base + 4 * PCL_PLANE_BYTES, p.vy + off, PCL_PLANE_BYTES, &s_bar[st]);
+        pcl_bulk_g2s(base + 5 * PCL_PLANE_BYTES, p.vz + off, PCL_PLANE_BYTES, &s_bar[st]);
+        if (WAVE) pcl_bulk_g2s(base + q_e * PCL_PLANE_BYTES, p.e + off, PCL_PLANE_BYTES, &s_bar[st]);
+        if (has_id) pcl_bulk_g2s(base + q_id * PCL_PLANE_BYTES, p.id + off, PCL_PLANE_BYTES, &s_bar[st]);
+        if (has_ns) pcl_bulk_g2s(base + q_ns * PCL_PLANE_BYTES, p.nscat + off, PCL_PLANE_BYTES, &s_bar[st]);
+    };
+    uint64_t tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = (int)(it & 1u);
+        const uint64_t next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) {
+            // the other stage was read (generic proxy) during the previous iteration, which ended with a
+            // CTA barrier; order those reads before the async-proxy writes of the new copy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next, st ^ 1);
         }
+        pcl_mbar_wait(&s_bar[st], (it >> 1) & 1u);
+        const unsigned char *base = s_stage_raw + (size_t)st * nplanes * PCL_PLANE_BYTES;
+        const float4 *f4 = reinterpret_cast<const float4 *>(base);
+        const int v = threadIdx.x;  // float4 index inside a plane
+        float4 x = f4[0 * PCL_BLOCK + v], y = f4[1 * PCL_BLOCK + v], z = f4[2 * PCL_BLOCK + v];
+        float4 vx = f4[3 * PCL_BLOCK + v], vy = f4[4 * PCL_BLOCK + v], vz = f4[5 * PCL_BLOCK + v];
+        float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (WAVE) e = f4[q_e * PCL_BLOCK + v];
+        const uint64_t i = tile * PCL_TILE_SLOTS + (uint64_t)v * 4;
+        uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
+        if (has_id) id = reinterpret_cast<const uint4 *>(base)[q_id * PCL_BLOCK + v];
+        uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
+        if (has_ns) nsc = reinterpret_cast<const uint4 *>(base)[q_ns * PCL_BLOCK + v];
+        pcl_step_group4<WAVE, DEL, false>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, zero4, zero4, zero4, cnt);
+        __syncthreads();  // every thread is done with this stage before it is refilled
+    }
+    // slots past the last full tile: register path, block 0 only (< 1024 slots)
+    if (blockIdx.x == 0) {
+        const uint64_t nvec = valid / 4;
+        for (uint64_t g = ntiles * PCL_BLOCK + threadIdx.x; g < nvec; g += PCL_BLOCK) {
+            const uint64_t i = g * 4;
+            float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
+            float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
+            float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (WAVE) e = pcl_ld4(p.e + i);
+            uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
+            if (has_id) id = pcl_ld4u(p.id + i);
+            uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
+            if (has_ns) nsc = pcl_ld4u(p.nscat + i);
+            pcl_step_group4<WAVE, DEL, false>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, zero4, zero4, zero4, cnt);
+        }
+        pcl_step_tail<WAVE, DEL, false>(p, K, nvec * 4, cnt);
     }
     pcl_flush_tally(cnt, row, K.nplanes);
 }
@@ -373,8 +507,8 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
             }
             uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
                                                    pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut, up, ur, cnt);
-            if (!DEL && (f & F_SCATTERED)) pcl_u4(nsc, l) += 1u;
-            if (!(f & (F_ABSORBED | F_ESCAPED))) keep |= 1u << l;
+            pcl_u4(nsc, l) += (!DEL && (f & F_SCATTERED)) ? 1u : 0u;
+            keep |= (f & (F_ABSORBED | F_ESCAPED)) ? 0u : (1u << l);
         }
         // tile-local rank of this thread's first survivor: shuffle scan inside the warp, warp totals
         // through shared memory
@@ -459,7 +593,7 @@ pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
             }
             float vx = 0.f, vy = 0.f, vz = 0.f;
             float e = WAVE ? p.e[i] : 1.f;
-            uint32_t f = pcl_scatter_one<WAVE, DEL>(p.dx[i], p.dy[i], p.dz[i], e, ut, up, ur, K.k, K.c, vx, vy, vz);
+            uint32_t f = pcl_scatter_one<WAVE, DEL>(true, p.dx[i], p.dy[i], p.dz[i], e, ut, up, ur, K.k, K.c, vx, vy, vz);
             if (f & F_SCATTERED) {
                 flag = 1;
                 cnt[C_SCAT] += 1u;
@@ -522,7 +656,7 @@ pcl_k_tally(pcl_soa p, StepK K, int64_t *row, uint64_t n) {
             dy = p.dy[i];
             dz = p.dz[i];
         }
-        pcl_tally_one(K, xx, p.y[i], p.z[i], dx, dy, dz, p.vx[i], p.vy[i], p.vz[i], cnt);
+        pcl_tally_one(K, true, xx, p.y[i], p.z[i], dx, dy, dz, p.vx[i], p.vy[i], p.vz[i], cnt);
     }
     pcl_flush_tally(cnt, row, K.nplanes);
 }
@@ -585,8 +719,23 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         return 0;
     }
     if (aligned) {
-        unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
-        pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row);
+        static int use_tma = -1;
+        if (use_tma < 0) {
+            const char *e = getenv("PCL_PHOTON_TMA");  // tuning aid: 0 = register-load kernel
+            use_tma = e ? atoi(e) : 1;
+        }
+        if (!INJ && use_tma) {
+            const int nplanes = 6 + (WAVE ? 1 : 0) + (p.id ? 1 : 0) + (p.nscat ? 1 : 0);
+            const size_t smem = (size_t)2 * nplanes * PCL_PLANE_BYTES;
+            auto kern = pcl_k_photon_step_tma<WAVE, DEL, PL>;
+            PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint64_t tiles = (p.n + PCL_TILE_SLOTS - 1) / PCL_TILE_SLOTS;
+            unsigned grid = (unsigned)(tiles < (uint64_t)ctx->sm_count * 4 ? (tiles ? tiles : 1) : (uint64_t)ctx->sm_count * 4);
+            kern<<<grid, PCL_BLOCK, smem, st>>>(p, K, row);
+        } else {
+            unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
+            pcl_k_photon_step<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, K, row);
+        }
         PCL_LAUNCHED(ctx);
     }
     if (!aligned) {  // scalar kernel for views that cannot take 128-bit accesses
