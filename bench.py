@@ -209,6 +209,10 @@ def photon_sim(n, rank, local, wavelength=False):
     import physicl_b200.newton
 
     sim = phys.Simulation(cl_on=True, device=local, seed=SEED, exit=lambda s: False)
+    if os.environ.get("PCL_FEEDBACK_EVERY"):  # tuning aids
+        sim.feedback_every = int(os.environ["PCL_FEEDBACK_EVERY"])
+    if os.environ.get("PCL_COMPACT_CADENCE"):
+        sim.compact_cadence = int(os.environ["PCL_COMPACT_CADENCE"])
     r = np.zeros((3, n), np.float32)
     v = np.zeros((3, n), np.float32)
     v[0] = C_LIGHT

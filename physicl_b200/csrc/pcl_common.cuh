@@ -16,7 +16,7 @@
 #endif
 // minimum resident CTAs per SM requested from ptxas for the fused photon kernels (register cap)
 #ifndef PCL_PHOTON_MINB
-#define PCL_PHOTON_MINB 4
+#define PCL_PHOTON_MINB 3
 #endif
 #define PCL_WARPS (PCL_BLOCK / 32)
 

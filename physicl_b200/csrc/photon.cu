@@ -304,15 +304,19 @@ __device__ __forceinline__ void pcl_mbar_wait(uint64_t *b, uint32_t parity) {
         : "memory");
 }
 
-#define PCL_TILE_SLOTS (PCL_BLOCK * 4)
-#define PCL_PLANE_BYTES (PCL_TILE_SLOTS * 4)
+#define PCL_WTILE_SLOTS 128                      /* one warp-tile: 4 photons per lane */
+#define PCL_WPLANE_BYTES (PCL_WTILE_SLOTS * 4)   /* 512 B of one plane */
 
+// Every WARP owns a two-stage ring (2 x planes x 512 B) and its own pair of mbarriers: lane 0 issues
+// the bulk copies of the warp's next 128-slot tile, the warp waits on its own barrier, and no warp
+// ever waits for another one (the first version used CTA-wide tiles and lost ~14 % of its issue
+// slots at the per-tile __syncthreads, see profiles/).
 template <bool WAVE, bool DEL, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
 pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     extern __shared__ __align__(128) unsigned char s_stage_raw[];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_bar[PCL_WARPS][2];
     uint32_t cnt[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) cnt[q] = 0u;
@@ -320,60 +324,63 @@ pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
     // plane order inside a stage: x y z vx vy vz [e] [id] [nscat]
     const int q_e = 6, q_id = 6 + (WAVE ? 1 : 0), q_ns = q_id + (has_id ? 1 : 0);
     const int nplanes = q_ns + (has_ns ? 1 : 0);
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint64_t valid = pcl_valid_slots(p);
-    const uint64_t ntiles = valid / PCL_TILE_SLOTS;
-    if (threadIdx.x == 0) {
-        pcl_mbar_init(&s_bar[0], 1);
-        pcl_mbar_init(&s_bar[1], 1);
+    const uint64_t ntiles = valid / PCL_WTILE_SLOTS;
+    uint64_t *bar = s_bar[wid];
+    unsigned char *ring = s_stage_raw + (size_t)wid * 2 * nplanes * PCL_WPLANE_BYTES;
+    if (lane == 0) {
+        pcl_mbar_init(&bar[0], 1);
+        pcl_mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    auto issue = [&](uint64_t tile, int st) {  // elected thread only
-        unsigned char *base = s_stage_raw + (size_t)st * nplanes * PCL_PLANE_BYTES;
-        const uint64_t off = tile * PCL_TILE_SLOTS;
-        pcl_mbar_expect_tx(&s_bar[st], (uint32_t)(nplanes * PCL_PLANE_BYTES));
-        pcl_bulk_g2s(base + 0 * PCL_PLANE_BYTES, p.x + off, PCL_PLANE_BYTES, &s_bar[st]);
-        pcl_bulk_g2s(base + 1 * PCL_PLANE_BYTES, p.y + off, PCL_PLANE_BYTES, &s_bar[st]);
-        pcl_bulk_g2s(base + 2 * PCL_PLANE_BYTES, p.z + off, PCL_PLANE_BYTES, &s_bar[st]);
-        pcl_bulk_g2s(base + 3 * PCL_PLANE_BYTES, p.vx + off, PCL_PLANE_BYTES, &s_bar[st]);
-        pcl_bulk_g2s(base + 4 * PCL_PLANE_BYTES, p.vy + off, PCL_PLANE_BYTES, &s_bar[st]);
-        pcl_bulk_g2s(base + 5 * PCL_PLANE_BYTES, p.vz + off, PCL_PLANE_BYTES, &s_bar[st]);
-        if (WAVE) pcl_bulk_g2s(base + q_e * PCL_PLANE_BYTES, p.e + off, PCL_PLANE_BYTES, &s_bar[st]);
-        if (has_id) pcl_bulk_g2s(base + q_id * PCL_PLANE_BYTES, p.id + off, PCL_PLANE_BYTES, &s_bar[st]);
-        if (has_ns) pcl_bulk_g2s(base + q_ns * PCL_PLANE_BYTES, p.nscat + off, PCL_PLANE_BYTES, &s_bar[st]);
+    __syncwarp();
+    auto issue = [&](uint64_t tile, int st) {  // lane 0 only
+        unsigned char *base = ring + (size_t)st * nplanes * PCL_WPLANE_BYTES;
+        const uint64_t off = tile * PCL_WTILE_SLOTS;
+        pcl_mbar_expect_tx(&bar[st], (uint32_t)(nplanes * PCL_WPLANE_BYTES));
+        pcl_bulk_g2s(base + 0 * PCL_WPLANE_BYTES, p.x + off, PCL_WPLANE_BYTES, &bar[st]);
+        pcl_bulk_g2s(base + 1 * PCL_WPLANE_BYTES, p.y + off, PCL_WPLANE_BYTES, &bar[st]);
+        pcl_bulk_g2s(base + 2 * PCL_WPLANE_BYTES, p.z + off, PCL_WPLANE_BYTES, &bar[st]);
+        pcl_bulk_g2s(base + 3 * PCL_WPLANE_BYTES, p.vx + off, PCL_WPLANE_BYTES, &bar[st]);
+        pcl_bulk_g2s(base + 4 * PCL_WPLANE_BYTES, p.vy + off, PCL_WPLANE_BYTES, &bar[st]);
+        pcl_bulk_g2s(base + 5 * PCL_WPLANE_BYTES, p.vz + off, PCL_WPLANE_BYTES, &bar[st]);
+        if (WAVE) pcl_bulk_g2s(base + q_e * PCL_WPLANE_BYTES, p.e + off, PCL_WPLANE_BYTES, &bar[st]);
+        if (has_id) pcl_bulk_g2s(base + q_id * PCL_WPLANE_BYTES, p.id + off, PCL_WPLANE_BYTES, &bar[st]);
+        if (has_ns) pcl_bulk_g2s(base + q_ns * PCL_WPLANE_BYTES, p.nscat + off, PCL_WPLANE_BYTES, &bar[st]);
     };
-    uint64_t tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+    const uint64_t nwarps = (uint64_t)gridDim.x * PCL_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * PCL_WARPS + wid;
+    if (lane == 0 && tile < ntiles) issue(tile, 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0; tile < ntiles; tile += nwarps, ++it) {
         const int st = (int)(it & 1u);
-        const uint64_t next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < ntiles) {
-            // the other stage was read (generic proxy) during the previous iteration, which ended with a
-            // CTA barrier; order those reads before the async-proxy writes of the new copy
+        const uint64_t next = tile + nwarps;
+        if (lane == 0 && next < ntiles) {
+            // the other stage was read (generic proxy) by this warp in the previous iteration, which
+            // ended with __syncwarp; order those reads before the async-proxy writes of the new copy
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(next, st ^ 1);
         }
-        pcl_mbar_wait(&s_bar[st], (it >> 1) & 1u);
-        const unsigned char *base = s_stage_raw + (size_t)st * nplanes * PCL_PLANE_BYTES;
+        pcl_mbar_wait(&bar[st], (it >> 1) & 1u);
+        const unsigned char *base = ring + (size_t)st * nplanes * PCL_WPLANE_BYTES;
         const float4 *f4 = reinterpret_cast<const float4 *>(base);
-        const int v = threadIdx.x;  // float4 index inside a plane
-        float4 x = f4[0 * PCL_BLOCK + v], y = f4[1 * PCL_BLOCK + v], z = f4[2 * PCL_BLOCK + v];
-        float4 vx = f4[3 * PCL_BLOCK + v], vy = f4[4 * PCL_BLOCK + v], vz = f4[5 * PCL_BLOCK + v];
+        float4 x = f4[0 * 32 + lane], y = f4[1 * 32 + lane], z = f4[2 * 32 + lane];
+        float4 vx = f4[3 * 32 + lane], vy = f4[4 * 32 + lane], vz = f4[5 * 32 + lane];
         float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (WAVE) e = f4[q_e * PCL_BLOCK + v];
-        const uint64_t i = tile * PCL_TILE_SLOTS + (uint64_t)v * 4;
+        if (WAVE) e = f4[q_e * 32 + lane];
+        const uint64_t i = tile * PCL_WTILE_SLOTS + (uint64_t)lane * 4;
         uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
-        if (has_id) id = reinterpret_cast<const uint4 *>(base)[q_id * PCL_BLOCK + v];
+        if (has_id) id = reinterpret_cast<const uint4 *>(base)[q_id * 32 + lane];
         uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
-        if (has_ns) nsc = reinterpret_cast<const uint4 *>(base)[q_ns * PCL_BLOCK + v];
+        if (has_ns) nsc = reinterpret_cast<const uint4 *>(base)[q_ns * 32 + lane];
+        __syncwarp();  // every lane has read its operands: the stage may be refilled
         pcl_step_group4<WAVE, DEL, false>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, zero4, zero4, zero4, cnt);
-        __syncthreads();  // every thread is done with this stage before it is refilled
     }
-    // slots past the last full tile: register path, block 0 only (< 1024 slots)
+    // slots past the last full warp-tile: register path, block 0 only (< 128 slots)
     if (blockIdx.x == 0) {
         const uint64_t nvec = valid / 4;
-        for (uint64_t g = ntiles * PCL_BLOCK + threadIdx.x; g < nvec; g += PCL_BLOCK) {
+        for (uint64_t g = ntiles * 32 + threadIdx.x; g < nvec; g += PCL_BLOCK) {
             const uint64_t i = g * 4;
             float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
             float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
@@ -726,10 +733,10 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         }
         if (!INJ && use_tma) {
             const int nplanes = 6 + (WAVE ? 1 : 0) + (p.id ? 1 : 0) + (p.nscat ? 1 : 0);
-            const size_t smem = (size_t)2 * nplanes * PCL_PLANE_BYTES;
+            const size_t smem = (size_t)2 * nplanes * PCL_WPLANE_BYTES * PCL_WARPS;
             auto kern = pcl_k_photon_step_tma<WAVE, DEL, PL>;
             PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint64_t tiles = (p.n + PCL_TILE_SLOTS - 1) / PCL_TILE_SLOTS;
+            const uint64_t tiles = (p.n + PCL_BLOCK * 4 - 1) / (PCL_BLOCK * 4);
             unsigned grid = (unsigned)(tiles < (uint64_t)ctx->sm_count * 4 ? (tiles ? tiles : 1) : (uint64_t)ctx->sm_count * 4);
             kern<<<grid, PCL_BLOCK, smem, st>>>(p, K, row);
         } else {
