@@ -18,7 +18,8 @@ escape + tallies) over every live photon.  metric = particle-steps/s, whole job.
              all host cores) on a bounded sample of the same workload
 
 Other workloads (--workload): kinematics_1m (configs[0], CUDA-graph stepped), kinematics_64m,
-wavelength_64m (configs[2]), gravity_256k (configs[3]); same JSON shape.
+kinematics_ref_64m, wavelength_64m (configs[2]), gravity_256k (configs[3]), sweep_1b (configs[4]);
+same JSON shape.
 """
 from __future__ import annotations
 
@@ -311,7 +312,9 @@ def bench_photon_sphere(args, rank, world, local):
                    "escaped_in_window": int(hist[-args.steps:].sum()) if len(hist) else 0},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "pcl_k_photon_step<0,0,0,0>",
+                     "traffic": 737.7e6, "traffic_note": "dram__bytes_read+write of one pcl_k_photon_step_tma launch over 16 Mi live "
+                     "photons (profiles/r1_ncu_full_photon_tma.csv): 44.0 B/photon vs 39.6 B algorithmic",
+                     "peak_source": peak_src, "kernel": "pcl_k_photon_step_tma<0,0,0> (+ pcl_k_photon_step_compact every m-th step)",
                      "algorithmic_bytes": "(36 + 12 f) B per live photon-step, f = scattered fraction (SURVEY.md 8d)",
                      "per_rank": True},
         "clocks": clocks.summary(),
@@ -422,6 +425,159 @@ def bench_gravity(args, rank, world, local):
     }
 
 
+def bench_wavelength(args, rank, world, local):
+    """configs[2]: Rayleigh (lambda^-4) scattering of photons whose energies follow the reference's binned
+    "Planck" law, sampled on the device; 64 Mi photons per GPU; no retirement (in-place WAVE kernel)."""
+    import torch
+
+    import physicl_b200 as phys
+    import physicl_b200.light
+    import physicl_b200.newton
+    from physicl_b200 import _capi
+
+    n = 64 * 2 ** 20
+    sim = phys.Simulation(cl_on=True, device=local, seed=2025, exit=lambda s: False)
+    ctx = sim.cl_ctx
+    dev = torch.device("cuda", local)
+    E_min = float(phys.light.E_from_wavelength(2500e-9))
+    E_max = float(phys.light.E_from_wavelength(200e-9))
+    e0ev, e1ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0ev.record()
+    e, E0 = phys.light.planck_sample_device(ctx, n, E_min, E_max, 5778.0, bins=50000, seed=2025, id_base=rank * n, device=dev)
+    e1ev.record()
+    torch.cuda.synchronize()
+    sample_ms = e0ev.elapsed_time(e1ev)
+    r = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v[0].fill_(C_LIGHT)
+    e = torch.nan_to_num(e.contiguous(), nan=0.5)  # the reference's "None" draws (mass of interval 0): mid-range energy
+    sim.add_particles(r, v, E=e, id_base=rank * n)
+    A, nd, dt = 5.1e-31 * (532e-9) ** 4, 2.5e25, 1e-5
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True))
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    sim.add_step(3, sign)
+    sim.device_store().group("photon").e0 = E0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sim.run_steps(args.warmup)
+        store = sim.store
+        row0 = store.current_row + 1
+        l0 = ctx.launches
+        barrier_sync(world)
+        ev0.record()
+        sim.run_steps(args.steps)
+        ev1.record()
+        barrier_sync(world)
+    ms = max_over_ranks(ev0.elapsed_time(ev1), world)
+    rows = np.array([store.read_row(q) for q in range(row0, store.current_row + 1)])
+    live, scat = float(rows[:, _capi.T_LIVE_IN].sum()), float(rows[:, _capi.T_SCATTERED].sum())
+    peak, peak_src = measured_peaks()
+    achieved = (40.0 * live + 12.0 * scat) / (ms * 1e-3) / 1e9
+    return {
+        "metric": "particle-steps/s", "value": sum_over_ranks(live, world) / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "wavelength_64m", "photons_per_gpu": n, "T": 5778.0, "bins": 50000, "A": A, "n": nd, "dt": dt,
+                   "planck_sampling_ms": sample_ms, "planck_sampling_gphotons_per_s": n / sample_ms / 1e6,
+                   "scattered_fraction": scat / max(live, 1), "l2": "state 1.75 GiB per GPU > L2"},
+        "e2e": None, "gpu_launches": int(ctx.launches - l0),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "pcl_k_photon_step_tma<1,0,0>",
+                     "algorithmic_bytes": "(36 + 12 f + 4) B per photon-step (SURVEY.md 8d, w = 1)", "per_rank": True},
+        "clocks": clocks.summary(),
+    }
+
+
+def bench_sweep_1b(args, rank, world, local):
+    """configs[4]: 2^30 particles in total, cut into contiguous blocks over the ranks (strong scaling):
+    K kinematics steps (v += a dt; dr = v dt; r += dr, 72 B/particle-step) then K photon-sphere steps."""
+    import torch
+
+    import physicl_b200 as phys
+    import physicl_b200.light
+    import physicl_b200.newton
+    from physicl_b200 import _capi
+    from physicl_b200.store import DeviceParticleStore
+
+    n_total = 2 ** 30
+    n = n_total // world
+    dev = torch.device("cuda", local)
+    ctx = _capi.Context(local)
+    # ---- kinematics -----------------------------------------------------------------------------
+    st = DeviceParticleStore(ctx)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    r = torch.empty((3, n), dtype=torch.float32, device=dev).uniform_(-1e3, 1e3, generator=gen)
+    v = torch.empty((3, n), dtype=torch.float32, device=dev).normal_(0, 10, generator=gen)
+    a = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    a[2].fill_(-9.81)
+    g = st.add_group("object", r, v, a=a, id_base=rank * n)
+    g.ensure("dx", "dy", "dz")
+    soa = g.soa()
+    for _ in range(args.warmup):
+        ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(DT), 1, None)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    barrier_sync(world)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(DT), 1, None)
+        ev1.record()
+        barrier_sync(world)
+    ms_kin = max_over_ranks(ev0.elapsed_time(ev1), world)
+    launches = ctx.launches - l0
+    del st, g, r, v, a, soa
+    torch.cuda.empty_cache()
+    # ---- photons ------------------------------------------------------------------------------
+    sim = phys.Simulation(cl_on=True, device=local, seed=SEED, exit=lambda s: False)
+    r = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v[0].fill_(C_LIGHT)
+    sim.add_particles(r, v, id_base=rank * n)
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(DT)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+    sim.add_step(3, phys.light.EscapeSphereStep(R_ESCAPE))
+    sim.add_step(4, phys.light.ScatterSignMeasureStep(None, True))
+    sim.run_steps(args.warmup)
+    store = sim.store
+    row0 = store.current_row + 1
+    l0 = sim.cl_ctx.launches
+    barrier_sync(world)
+    ev0.record()
+    sim.run_steps(args.steps)
+    ev1.record()
+    barrier_sync(world)
+    ms_ph = max_over_ranks(ev0.elapsed_time(ev1), world)
+    launches += sim.cl_ctx.launches - l0
+    rows = np.array([store.read_row(q) for q in range(row0, store.current_row + 1)])
+    rows = rows[rows[:, _capi.T_LIVE_IN] > 0]
+    live, scat = float(rows[:, _capi.T_LIVE_IN].sum()), float(rows[:, _capi.T_SCATTERED].sum())
+    live_all = sum_over_ranks(live, world)
+    kin_units = float(n_total) * args.steps
+    peak, peak_src = measured_peaks()
+    kin_gbs = 72.0 * n * args.steps / (ms_kin * 1e-3) / 1e9
+    ph_gbs = (36.0 * live + 12.0 * scat) / (ms_ph * 1e-3) / 1e9
+    return {
+        "metric": "particle-steps/s", "value": (kin_units + live_all) / ((ms_kin + ms_ph) * 1e-3), "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (ms_kin + ms_ph) / (2 * args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (generated on device)",
+        "config": {"workload": "sweep_1b", "particles_total": n_total, "particles_per_gpu": n,
+                   "kinematics": {"particle_steps_per_s": kin_units / (ms_kin * 1e-3), "ms_per_step": ms_kin / args.steps,
+                                  "hbm_gbs_per_gpu": kin_gbs, "frac": kin_gbs / peak},
+                   "photon_sphere": {"particle_steps_per_s": live_all / (ms_ph * 1e-3), "ms_per_step": ms_ph / args.steps,
+                                     "hbm_gbs_per_gpu": ph_gbs, "frac": ph_gbs / peak}},
+        "e2e": None, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": kin_gbs, "peak": peak, "unit": "GB/s", "frac": kin_gbs / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "pcl_k_kinematics<1,true>", "algorithmic_bytes": "72 B per particle-step",
+                     "per_rank": True},
+        "clocks": clocks.summary(),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -429,7 +585,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="photon_sphere_16m",
-                    choices=["photon_sphere_16m", "kinematics_1m", "kinematics_64m", "kinematics_ref_64m", "gravity_256k"])
+                    choices=["photon_sphere_16m", "kinematics_1m", "kinematics_64m", "kinematics_ref_64m", "gravity_256k",
+                             "wavelength_64m", "sweep_1b"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
@@ -450,6 +607,10 @@ def main():
         out = bench_kinematics(args, rank, world, local, 64 * 2 ** 20, True, False)
     elif args.workload == "kinematics_ref_64m":
         out = bench_kinematics(args, rank, world, local, 64 * 2 ** 20, False, False)
+    elif args.workload == "wavelength_64m":
+        out = bench_wavelength(args, rank, world, local)
+    elif args.workload == "sweep_1b":
+        out = bench_sweep_1b(args, rank, world, local)
     else:
         out = bench_gravity(args, rank, world, local)
     if rank == 0:

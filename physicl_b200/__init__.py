@@ -272,6 +272,10 @@ class Simulation(threading.Thread):
                 a = np.array([np.asarray(o.a, np.float64) for o in mine]).reshape(-1, 3).T
                 store.add_group(kind, r, v, E=E, a=a if np.any(a) else None, id_base=lo, host_objs=mine)
         for kind, p in (self._pending or {}).items():
+            if hasattr(p["r"], "is_cuda") and p["r"].is_cuda:  # device tensors: this rank's block as is
+                store.add_group(kind, p["r"], p["v"], E=p["E"], a=p["a"], id_base=int(p["id_base"] or 0),
+                                track_nscat=p["track_nscat"])
+                continue
             r = np.asarray(p["r"]).reshape(3, -1)
             lo, hi = self._shard_slice(r.shape[1]) if p["id_base"] is None else (0, r.shape[1])
             sl = slice(lo, hi)

@@ -73,6 +73,15 @@ class Group:
 
     def upload(self, name, host):
         torch = _torch()
+        if isinstance(host, torch.Tensor) and host.is_cuda:
+            # adopt a device tensor as the plane (bulk set-ups that never touch the host)
+            want = torch.int32 if name in _PLANES_U32 else torch.float32
+            assert host.dtype == want and host.is_contiguous() and host.numel() == self.n, (name, host.dtype, host.shape)
+            assert host.data_ptr() % 16 == 0, "device planes must be 16-byte aligned"
+            self.planes[name] = host
+            if name == "id":
+                self.id_valid[self.cur] = True
+            return
         if name in _PLANES_U32:
             arr = np.ascontiguousarray(host, np.uint32).view(np.int32)
         else:
@@ -141,8 +150,11 @@ class DeviceParticleStore:
     # ---- construction -----------------------------------------------------------------------
     def add_group(self, kind, r, v, E=None, a=None, id_base=0, host_objs=None, track_nscat=False):
         """r, v, a: (3, N) array-likes in code units; E: (N,) or None."""
-        r = np.asarray(r).reshape(3, -1)
-        v = np.asarray(v).reshape(3, -1)
+        torch = _torch()
+        on_device = isinstance(r, torch.Tensor) and r.is_cuda
+        if not on_device:
+            r = np.asarray(r).reshape(3, -1)
+            v = np.asarray(v).reshape(3, -1)
         n = r.shape[1]
         if kind in self.groups:
             raise ValueError("group '%s' already present; build the store once from all particles" % kind)
@@ -154,10 +166,14 @@ class DeviceParticleStore:
         for i, nm in enumerate(("vx", "vy", "vz")):
             g.upload(nm, v[i])
         if a is not None:
-            a = np.asarray(a).reshape(3, -1)
+            if not on_device:
+                a = np.asarray(a).reshape(3, -1)
             for i, nm in enumerate(("ax", "ay", "az")):
                 g.upload(nm, a[i])
-        if E is not None:
+        if E is not None and isinstance(E, torch.Tensor) and E.is_cuda:
+            g.e0 = 1.0  # the caller supplies e = E / E0 and sets g.e0 itself
+            g.upload("e", E)
+        elif E is not None:
             E = np.asarray(E, np.float64).reshape(-1)
             finite = E[np.isfinite(E)]
             g.e0 = float(np.max(np.abs(finite))) if finite.size and np.max(np.abs(finite)) > 0 else 1.0
