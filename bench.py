@@ -267,35 +267,44 @@ def bench_photon_sphere(args, rank, world, local):
             raise RuntimeError("skipped (--no-e2e)")
         host = {k: torch.zeros(n, dtype=torch.float32).pin_memory() for k in ("x", "y", "z", "vx", "vy", "vz")}
         host["vx"].fill_(C_LIGHT)
+        host["id"] = torch.arange(n, dtype=torch.int32).pin_memory()
         soa = _capi.Soa()
-        soa.n = n
         for k, t in host.items():
             setattr(soa, k, t.data_ptr())
         soa.id_base = rank * n
         sp = _capi.ScatterParams(k=A_N, c=C_LIGHT, mode=0)
         pl = _capi.make_planes([])
         row = np.zeros(_capi.TALLY_COLS, np.int64)
+        n_out = C.c_uint64(0)
         k_e2e = max(3, min(args.steps, 20))
+        state = {"n": n, "up": 0, "down": 0}
 
         def host_step(s):
+            # photons live in pinned HOST planes between steps; survivors come back densely (remove_obj)
+            soa.n = state["n"]
             rg = _capi.Rng(seed=SEED, step=s)
-            ctx.call("pcl_photon_step_host", C.byref(soa), C.c_float(DT), C.byref(sp), C.byref(rg), C.c_float(R_ESCAPE ** 2),
-                     C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(1 << 20))
+            ctx.call("pcl_photon_step_host_compact", C.byref(soa), C.c_float(DT), C.byref(sp), C.byref(rg),
+                     C.c_float(R_ESCAPE ** 2), C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(1 << 20), C.byref(n_out))
+            state["up"] += 28 * state["n"]
+            state["down"] += 28 * n_out.value + 8 * _capi.TALLY_COLS
+            state["n"] = n_out.value
             return int(row[_capi.T_LIVE_IN])
 
-        for s in range(3):
+        for s in range(args.warmup):
             host_step(s)
+        state["up"] = state["down"] = 0
         barrier_sync(world)
         t0 = time.perf_counter()
         live_e = 0
-        for s in range(3, 3 + k_e2e):
+        for s in range(args.warmup, args.warmup + k_e2e):
             live_e += host_step(s)
         barrier_sync(world)
         wall = max_over_ranks(time.perf_counter() - t0, world)
         e2e = {"value": sum_over_ranks(float(live_e), world) / wall, "unit": "particle-steps/s",
-               "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 8 * _capi.TALLY_COLS, "steps": k_e2e,
+               "h2d_bytes_per_step": state["up"] // k_e2e, "d2h_bytes_per_step": state["down"] // k_e2e, "steps": k_e2e,
                "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
-               "path": "pcl_photon_step_host: pinned host SoA planes -> chunked H2D -> fused kernel -> D2H"}
+               "path": "pcl_photon_step_host_compact: pinned host SoA planes (r, v, id) -> chunked H2D -> fused "
+                       "retire-and-compact kernel -> D2H of the survivors, 4 streams"}
     except Exception as e:  # report, never hide
         e2e = {"value": None, "unit": "particle-steps/s", "error": repr(e)}
 

@@ -209,6 +209,13 @@ int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *po
 int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
                          const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
                          int64_t *tally_row_host, uint64_t chunk);
+/* Same, with Simulation.remove_obj folded in: only the survivors come back, written densely from the
+ * front of the host planes (host->id is required: ids identify photons afterwards); *n_out_host =
+ * survivors.  PCIe bytes are proportional to live photons (28 B up + 28 B down each). */
+int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt,
+                                 const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                                 const pcl_planes *planes, int64_t *tally_row_host, uint64_t chunk,
+                                 uint64_t *n_out_host);
 int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes);
 int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
 

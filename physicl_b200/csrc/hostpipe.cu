@@ -11,13 +11,16 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
                          int64_t *tally_row, uint64_t *n_out);
 
-#define PIPE_SLOTS 3
+#define PIPE_SLOTS 4
 #define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
 
 struct pcl_hostpipe {
     uint64_t chunk;
     cudaStream_t stream[PIPE_SLOTS];
     float *buf[PIPE_SLOTS][12];
+    float *out[PIPE_SLOTS][9];  // compacting form: survivors of the chunk (x y z vx vy vz e id nscat)
+    uint64_t *cnt_dev;          // [PIPE_SLOTS] survivors per in-flight chunk
+    uint64_t *cnt_pinned;       // [PIPE_SLOTS]
     int64_t *tally_dev;
     int64_t *tally_pinned;
 };
@@ -29,7 +32,11 @@ void pcl_hostpipe_destroy(pcl_ctx *ctx) {
         if (hp->stream[s]) cudaStreamDestroy(hp->stream[s]);
         for (int q = 0; q < 12; ++q)
             if (hp->buf[s][q]) cudaFree(hp->buf[s][q]);
+        for (int q = 0; q < 9; ++q)
+            if (hp->out[s][q]) cudaFree(hp->out[s][q]);
     }
+    if (hp->cnt_dev) cudaFree(hp->cnt_dev);
+    if (hp->cnt_pinned) cudaFreeHost(hp->cnt_pinned);
     if (hp->tally_dev) cudaFree(hp->tally_dev);
     if (hp->tally_pinned) cudaFreeHost(hp->tally_pinned);
     free(hp);
@@ -121,5 +128,89 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
     for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
     PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compacting host-buffer step: same timestep, but each chunk runs the retire-and-compact kernel and
+// only the SURVIVORS travel back, written densely from the front of the host planes (the host-side
+// meaning of the reference's sim.remove_obj, physicl/__init__.py:455-459).  PCIe bytes per step are
+// proportional to live photons: 28 B up + 28 B down each (r, v, id).  Chunks are completed in order
+// so the output offset is a running sum of survivor counts; an output region never overtakes a chunk
+// that has not been uploaded yet because a chunk yields at most as many photons as it received.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                                            const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                                            int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, host && sp && rng && tally_row_host && n_out_host, "null argument");
+    PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz && host->id,
+                "r, v and id planes are required (ids travel with the photons)");
+    PCL_REQUIRE(ctx, rng->u_rand == nullptr, "the compacting host step draws from Philox");
+    if (chunk == 0) chunk = 1u << 20;
+    chunk = (chunk + 3) & ~(uint64_t)3;
+    int rc = pipe_prepare(ctx, chunk);
+    if (rc) return rc;
+    pcl_hostpipe *hp = ctx->pipe;
+    const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH;
+    if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
+    if (!hp->cnt_dev) {
+        PCL_CUDA(ctx, cudaMalloc(&hp->cnt_dev, PIPE_SLOTS * sizeof(uint64_t)));
+        PCL_CUDA(ctx, cudaMallocHost(&hp->cnt_pinned, PIPE_SLOTS * sizeof(uint64_t)));
+        for (int s = 0; s < PIPE_SLOTS; ++s)
+            for (int q = 0; q < 9; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->out[s][q], chunk * sizeof(float)));
+    }
+    PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
+    PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[0]));
+    const uint64_t nchunks = (host->n + chunk - 1) / chunk;
+    uint64_t out_off = 0;
+    // planes that travel: index into buf/out
+    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, wave ? host->e : nullptr,
+                        (float *)host->id, (float *)host->nscat};
+    auto complete = [&](uint64_t c) -> int {  // read the survivor count of chunk c, queue its D2H copies
+        const int s = (int)(c % PIPE_SLOTS);
+        cudaStream_t st = hp->stream[s];
+        PCL_CUDA(ctx, cudaStreamSynchronize(st));
+        const uint64_t cnt = hp->cnt_pinned[s];
+        for (int q = 0; q < 9; ++q)
+            if (hplane[q] && cnt)
+                PCL_CUDA(ctx, cudaMemcpyAsync(hplane[q] + out_off, hp->out[s][q], cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        out_off += cnt;
+        return 0;
+    };
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % PIPE_SLOTS);
+        cudaStream_t st = hp->stream[s];
+        const uint64_t off = c * chunk;
+        const uint64_t m = (host->n - off < chunk) ? host->n - off : chunk;
+        pcl_soa src, dst;
+        memset(&src, 0, sizeof(src));
+        memset(&dst, 0, sizeof(dst));
+        src.n = dst.n = m;
+        src.id_base = dst.id_base = host->id_base;
+        float **in = hp->buf[s], **ou = hp->out[s];
+        for (int q = 0; q < 9; ++q)
+            if (hplane[q]) PCL_CUDA(ctx, cudaMemcpyAsync(in[q], hplane[q] + off, m * sizeof(float), cudaMemcpyHostToDevice, st));
+        src.x = in[0]; src.y = in[1]; src.z = in[2]; src.vx = in[3]; src.vy = in[4]; src.vz = in[5];
+        dst.x = ou[0]; dst.y = ou[1]; dst.z = ou[2]; dst.vx = ou[3]; dst.vy = ou[4]; dst.vz = ou[5];
+        if (wave) { src.e = in[6]; dst.e = ou[6]; }
+        src.id = (uint32_t *)in[7]; dst.id = (uint32_t *)ou[7];
+        if (host->nscat) { src.nscat = (uint32_t *)in[8]; dst.nscat = (uint32_t *)ou[8]; }
+        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s);
+        if (rc) return rc;
+        PCL_CUDA(ctx, cudaMemcpyAsync(hp->cnt_pinned + s, hp->cnt_dev + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (c + 1 >= PIPE_SLOTS) {  // oldest chunk in flight: its slot is needed next
+            rc = complete(c + 1 - PIPE_SLOTS);
+            if (rc) return rc;
+        }
+    }
+    for (uint64_t c = (nchunks >= PIPE_SLOTS ? nchunks - PIPE_SLOTS + 1 : 0); c < nchunks; ++c) {
+        rc = complete(c);
+        if (rc) return rc;
+    }
+    for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
+    PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
+    *n_out_host = out_off;
     return 0;
 }

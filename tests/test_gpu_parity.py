@@ -568,3 +568,42 @@ def test_pingpong_loop_equals_in_place_loop(ctx):
         assert np.array_equal(sa["id"], sb["id"])
         for nm in u.PLANE_NAMES:
             assert u.same_bits(sa[nm], sb[nm]), (m, nm)
+
+
+def test_compacting_host_step_equals_resident_steps(ctx):
+    """pcl_photon_step_host_compact: photons in pinned host planes, survivors returned densely; same
+    tallies and the same survivors (by id) as the device-resident path."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 400_003
+    r, v = u.beam_photons(n)
+    st, g = u.make_store(ctx, r, v, id_base=7_000_000)
+    host = {nm: torch.from_numpy(g.download(nm).copy()).pin_memory() for nm in u.PLANE_NAMES}
+    host["id"] = torch.arange(n, dtype=torch.int32).pin_memory()
+    dt, k, c, r2 = 1e-3, 1e-6, u.C_LIGHT, 1.0e6 ** 2
+    n_live = n
+    for step in range(8):
+        want = u.photon_step(ctx, st, g, dt, k, c, 0, seed=9, step=step, r2_escape=r2, planes=[(0, 7.0e5)])
+        soa = _capi.Soa()
+        soa.n = n_live
+        soa.id_base = 7_000_000
+        for nm, t in host.items():
+            setattr(soa, nm, t.data_ptr())
+        sp = _capi.ScatterParams(k=k, c=c, mode=0)
+        rg = _capi.Rng(seed=9, step=step)
+        pl = _capi.make_planes([(0, 7.0e5)])
+        row = np.zeros(_capi.TALLY_COLS, np.int64)
+        n_out = C.c_uint64(0)
+        ctx.call("pcl_photon_step_host_compact", C.byref(soa), C.c_float(dt), C.byref(sp), C.byref(rg), C.c_float(r2),
+                 C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(65_536), C.byref(n_out))
+        assert np.array_equal(row, want), (step, row, want)
+        n_live = int(n_out.value)
+        assert n_live == int(want[_capi.T_ALIVE])
+    assert 0 < n_live < n
+    snap = st.snapshot("photon")
+    ids = host["id"].numpy()[:n_live].view(np.uint32)
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], snap["id"])
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(host[nm].numpy()[:n_live][order], snap[nm]), nm

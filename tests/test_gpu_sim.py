@@ -250,3 +250,102 @@ def test_bulk_run_steps_equals_threaded_run():
     for nm in ("x", "y", "z", "vx", "vy", "vz"):
         assert np.array_equal(pa[nm].view(np.uint32), pb[nm].view(np.uint32)), nm
     assert x.cl_ctx.launches <= a.cl_ctx.launches
+
+
+def _sphere_run(n, steps, seed, A, nd, R, dt=0.001):
+    x = phys.Simulation(cl_on=True, seed=seed)
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x.add_particles(r, v, track_nscat=True)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sc = phys.light.ScatterIsotropicStep(A=A, n=nd)
+    x.add_step(2, sc)
+    esc = None
+    if R:
+        esc = phys.light.EscapeSphereStep(R)
+        x.add_step(3, esc)
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(4, sign)
+    x.run_steps(steps)
+    return x, sc, esc, sign
+
+
+def test_escape_histogram_matches_float64_reference_law():
+    """configs[1] in small: the escape-time histogram and the per-step tallies of the device run
+    against the reference's law in float64 (oracle.photon_step_f64) driven by the same Philox
+    uniforms.  Decisions can only differ where |pcoll - rand| or |r| - R is within float32 rounding,
+    so the integer rows agree up to a handful of photons out of 300 000."""
+    import oracle
+
+    n, steps, R = 300_000, 40, 1.5e6
+    x, sc, esc, sign = _sphere_run(n, steps, seed=31, A=np.double(1e-3), nd=np.double(1e-3), R=R)
+    seed = sc._seed(x)
+    st = {k: np.zeros(n) for k in ("x", "y", "z", "vx", "vy", "vz")}
+    st["vx"][:] = float(phys.light.c)
+    rows = np.array([oracle.photon_step_f64(st, 1e-3, 1e-3, 1e-3, 0.0, float(phys.light.c), 0, seed, s, R * R) for s in range(steps)])
+    got_esc = esc.escaped
+    got = np.array(sign.data)
+    assert got_esc.sum() > 0.5 * n
+    assert np.abs(got_esc - rows[:, oracle.T_ESCAPED]).max() <= 3
+    assert np.abs(got[:, 1] - rows[:, oracle.T_ALIVE]).max() <= 5
+    for col, ocol in ((2, oracle.T_XP), (3, oracle.T_YP), (4, oracle.T_ZP)):
+        assert np.abs(got[:, col] - rows[:, ocol]).max() <= 5
+
+
+def test_scatter_count_per_photon_is_binomial():
+    """With a constant collision probability p the number of scatterings of a photon after s steps
+    is Binomial(s, p): chi-square of the device's nscat histogram at n = 500 000 (config 3's
+    scatter-count check), plus the mean against s*p at 5 sigma."""
+    from scipy import stats
+
+    n, steps = 500_000, 12
+    x, sc, _, _ = _sphere_run(n, steps, seed=8, A=np.double(1e-3), nd=np.double(1e-3), R=None)
+    ns = x.store.snapshot("photon")["nscat"].astype(np.int64)
+    p = float(np.float32(1e-6) * np.float32(np.float32(float(phys.light.c)) * np.float32(1e-3)))
+    assert abs(ns.mean() - steps * p) < 5 * np.sqrt(steps * p * (1 - p) / n)
+    obs = np.bincount(ns, minlength=steps + 1)[: steps + 1].astype(float)
+    exp = stats.binom.pmf(np.arange(steps + 1), steps, p) * n
+    keep = exp >= 5
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum() + (obs[~keep].sum() - exp[~keep].sum()) ** 2 / max(exp[~keep].sum(), 1e-9)
+    assert stats.chi2.sf(chi2, keep.sum()) > 1e-4, chi2
+
+
+def test_code_scaled_units_give_the_same_physics():
+    """set_code_scale changes every number the kernels see (c, A, n, dt-products; reference light.py:14,
+    :309) but not the dimensionless collision probability: tallies agree between metres and kilometres."""
+    import importlib
+    import subprocess
+    import sys
+    import json
+    import os
+
+    prog = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+import physicl_b200 as phys
+scale = float(sys.argv[1])
+phys.Measurement.set_code_scale("m", scale)
+import physicl_b200.light, physicl_b200.newton
+x = phys.Simulation(cl_on=True, seed=4)
+n = 50000
+c = float(phys.light.c)
+r = np.zeros((3, n)); v = np.zeros((3, n)); v[0] = c
+x.add_particles(r, v)
+x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+x.add_step(1, phys.newton.NewtonianKinematicsStep())
+x.add_step(2, phys.light.ScatterIsotropicStep(A=phys.Measurement(1e-3, "m**2"), n=phys.Measurement(1e-3, "m**-3")))
+m = phys.light.ScatterSignMeasureStep(None, True)
+x.add_step(3, m)
+x.run_steps(10)
+print(json.dumps({"c": c, "rows": np.array(m.data)[:, 1:].tolist()}))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for scale in ("1.0", "0.001"):
+        r = subprocess.run([sys.executable, "-c", prog, scale], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert out[0]["c"] == 299792458.0 and abs(out[1]["c"] - 299792.458) < 1e-6
+    a, b = np.array(out[0]["rows"]), np.array(out[1]["rows"])
+    assert a.shape == b.shape and np.abs(a - b).max() <= 3  # float32 rounding may flip a decision or two
