@@ -302,7 +302,11 @@ class Simulation(threading.Thread):
         for kind, g in st.groups.items():
             if kind == "photon" and getattr(self, "_live_row", None) is not None:
                 n_live = int(st.peek_row(self._live_row)[0])
-                st.maybe_compact("photon", n_live)
+                # get_state() may call this from another thread while the simulation thread is stepping
+                # (physicl/__init__.py:532-541 takes the lock only on request): only the owner of the
+                # stepping loop may move planes around
+                if not self.running or threading.current_thread() is self:
+                    st.maybe_compact("photon", n_live)
                 n += n_live
             else:
                 n += g.n_live
