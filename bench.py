@@ -70,6 +70,9 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:  # nvidia-smi needs a moment to start sampling
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self

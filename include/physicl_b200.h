@@ -192,10 +192,13 @@ int pcl_planck_sample(pcl_ctx *ctx, uintptr_t stream, uint64_t n, uint64_t id_ba
 
 /* All-pairs gravity (not in the reference; behind the Step API): for local bodies i in
  * [0, n_local) a_i = G * sum_j m_j (r_j - r_i) / (|r_ij|^2 + eps2)^(3/2) over posm_all[0..n_total),
- * float4 = (x, y, z, m).  posm_local are the i-bodies. Writes ax, ay, az. */
+ * float4 = (x, y, z, m).  posm_local are the i-bodies. Writes ax, ay, az (adds when accumulate).
+ * j-bodies with index in [j_skip_begin, j_skip_end) are left out: a sharded caller accumulates its
+ * own block while the all-gather is in flight, then everything else from the gathered array. */
 int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
                       const float *posm_all, uint64_t n_total, float G, float eps2, float *ax,
-                      float *ay, float *az, int accumulate);
+                      float *ay, float *az, int accumulate, uint64_t j_skip_begin,
+                      uint64_t j_skip_end);
 /* kick-drift for gravity bodies: v += a*dt; r += v*dt on the packed posm (x,y,z,m); x,y,z
  * (nullable triple) are the store's SoA position planes, refreshed in the same pass. */
 int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx,

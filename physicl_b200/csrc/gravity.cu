@@ -136,10 +136,16 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return d;
 }
 
+// grid = (i tiles, j splits): when there are few i-bodies per GPU (strong scaling: 32 Ki at 8 GPUs is
+// only 128 i-tiles for 148 SMs) the j range is cut into gridDim.y pieces and each CTA writes a partial
+// sum to `part[(split*3 + comp)*n_local + i]`; pcl_k_gravity_reduce adds the pieces in a fixed order,
+// so the result does not depend on scheduling.  Bodies in [skip_lo, skip_hi) are left out (the rank's
+// own block, already accumulated while the all-gather was in flight).
 template <int IB, int T, int JT>
 __global__ void __launch_bounds__(T)
 pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__restrict__ pj, uint64_t n_total,
-                 float G, float eps2, float *ax, float *ay, float *az, int accumulate) {
+                 float G, float eps2, float *ax, float *ay, float *az, int accumulate, uint64_t skip_lo, uint64_t skip_hi,
+                 float *part) {
     constexpr int NP = JT / 2;            // j pairs per tile
     constexpr int LP = (NP + T - 1) / T;  // pairs loaded per thread per tile
     __shared__ ulonglong2 s_a[2][NP];     // (x0,x1), (y0,y1)
@@ -156,17 +162,26 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
         axi[m] = ayi[m] = azi[m] = pk(0.f, 0.f);
     }
     const f32x2 eps = pk(eps2, eps2);
-    const uint64_t ntile = (n_total + JT - 1) / JT;
+    const uint64_t ntile_all = (n_total + JT - 1) / JT;
+    // tiles lying entirely inside the skip range form one contiguous run [sk0, sk1): the j splits share
+    // only the remaining ("live") tiles, so every split has the same amount of work
+    const uint64_t sk0 = (skip_lo + JT - 1) / JT, sk1r = skip_hi / JT;
+    const uint64_t nskip = (skip_hi > skip_lo && sk1r > sk0) ? sk1r - sk0 : 0;
+    const uint64_t nlive = ntile_all - nskip;
+    const uint64_t k_begin = nlive * blockIdx.y / gridDim.y, k_end = nlive * (blockIdx.y + 1) / gridDim.y;
+    auto tile_of = [&](uint64_t k) { return k < sk0 ? k : k + nskip; };
     float4 r0[LP], r1[LP];  // next tile, register staged
+    auto live_j = [&](uint64_t j) { return j < n_total && !(j >= skip_lo && j < skip_hi); };
     auto fetch = [&](uint64_t t) {
 #pragma unroll
         for (int u = 0; u < LP; ++u) {
             const int q = threadIdx.x + u * T;
             const uint64_t j = t * JT + 2 * (uint64_t)q;
-            r0[u] = (q < NP && j < n_total) ? pj[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[u] = (q < NP && j + 1 < n_total) ? pj[j + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            r0[u] = (q < NP && live_j(j)) ? pj[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[u] = (q < NP && live_j(j + 1)) ? pj[j + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
+
     auto stage = [&](int buf) {
 #pragma unroll
         for (int u = 0; u < LP; ++u) {
@@ -177,12 +192,14 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
             }
         }
     };
-    fetch(0);
-    stage(0);
+    if (k_begin < k_end) {
+        fetch(tile_of(k_begin));
+        stage(0);
+    }
     __syncthreads();
-    for (uint64_t t = 0; t < ntile; ++t) {
-        const int buf = (int)(t & 1);
-        if (t + 1 < ntile) fetch(t + 1);  // global loads in flight while this tile is consumed
+    int buf = 0;
+    for (uint64_t k = k_begin; k < k_end; ++k, buf ^= 1) {
+        if (k + 1 < k_end) fetch(tile_of(k + 1));  // global loads in flight while this tile is consumed
 #pragma unroll 4
         for (int q = 0; q < NP; ++q) {
             const ulonglong2 A = s_a[buf][q], B = s_b[buf][q];
@@ -203,7 +220,7 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
                 azi[m] = fma2(sc, dz, azi[m]);
             }
         }
-        if (t + 1 < ntile) stage(buf ^ 1);
+        if (k + 1 < k_end) stage(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
@@ -214,6 +231,12 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
             upk(axi[m], a0, a1);
             upk(ayi[m], b0, b1);
             upk(azi[m], c0, c1);
+            if (part) {  // un-scaled partial sums of this j split; reduced in a fixed order afterwards
+                part[((uint64_t)blockIdx.y * 3 + 0) * n_local + i] = a0 + a1;
+                part[((uint64_t)blockIdx.y * 3 + 1) * n_local + i] = b0 + b1;
+                part[((uint64_t)blockIdx.y * 3 + 2) * n_local + i] = c0 + c1;
+                continue;
+            }
             float gx = G * (a0 + a1), gy = G * (b0 + b1), gz = G * (c0 + c1);
             if (accumulate) {
                 gx += ax[i];
@@ -227,13 +250,37 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
     }
 }
 
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_gravity_reduce(const float *__restrict__ part, uint32_t nsplit, uint64_t n_local, float G, float *ax, float *ay,
+                     float *az, int accumulate) {
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n_local; i += stride) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (uint32_t q = 0; q < nsplit; ++q) {
+            sx += part[((uint64_t)q * 3 + 0) * n_local + i];
+            sy += part[((uint64_t)q * 3 + 1) * n_local + i];
+            sz += part[((uint64_t)q * 3 + 2) * n_local + i];
+        }
+        float gx = G * sx, gy = G * sy, gz = G * sz;
+        if (accumulate) {
+            gx += ax[i];
+            gy += ay[i];
+            gz += az[i];
+        }
+        ax[i] = gx;
+        ay[i] = gy;
+        az[i] = gz;
+    }
+}
+
 extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
                                  const float *posm_all, uint64_t n_total, float G, float eps2, float *ax, float *ay,
-                                 float *az, int accumulate) {
+                                 float *az, int accumulate, uint64_t j_skip_begin, uint64_t j_skip_end) {
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, posm_local && posm_all && ax && ay && az, "null argument");
     PCL_REQUIRE(ctx, pcl_aligned16(posm_local) && pcl_aligned16(posm_all), "posm arrays must be 16-byte aligned");
     PCL_REQUIRE(ctx, eps2 > 0.f, "softening eps2 must be > 0 (the i == j term relies on it)");
+    PCL_REQUIRE(ctx, j_skip_begin <= j_skip_end, "bad skip range");
     if (n_local == 0 || n_total == 0) return 0;
     // Tile shape: IB i-bodies per thread x T threads per CTA.  Small CTAs keep the number of CTAs per
     // SM nearly uniform (262144 bodies -> 1024 CTAs of 256 bodies: 6.9 per SM), which matters because
@@ -247,9 +294,36 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
 #define PCL_GRAV(IB, T)                                                                                       \
     pcl_k_gravity<IB, T><<<(unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), T, 0, st>>>(                  \
         (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
+    if (variant >= 1 && variant <= 7)
+        PCL_REQUIRE(ctx, j_skip_begin == j_skip_end, "the scalar tuning variants do not implement the skip range");
+    // j splits: enough CTAs for ~4 per SM, at least 2 tiles of 512 bodies per split
+    float *part = nullptr;
+    unsigned nsplit = 1;
+    {
+        const uint64_t itiles = (n_local + 255) / 256, jtiles = (n_total + 511) / 512;
+        // 7 CTAs of 4 warps per SM is what the register budget admits: cut j so that all CTAs fit in ONE
+        // wave (floor, not ceil: a second, mostly empty wave costs more than a slightly emptier first one)
+        uint64_t want = ((uint64_t)ctx->sm_count * 7) / itiles;
+        if (want < 1) want = 1;
+        if (want > jtiles / 2) want = jtiles / 2;
+        if (want > 64) want = 64;
+        if (want > 1 && (variant == 0 || variant >= 10)) {
+            nsplit = (unsigned)want;
+            const size_t need = (size_t)nsplit * 3 * n_local;
+            if (ctx->grav_cap < need) {
+                if (ctx->grav_part) PCL_CUDA(ctx, cudaFree(ctx->grav_part));
+                ctx->grav_part = nullptr;
+                ctx->grav_cap = 0;
+                PCL_CUDA(ctx, cudaMalloc(&ctx->grav_part, need * sizeof(float)));
+                ctx->grav_cap = need;
+            }
+            part = ctx->grav_part;
+        }
+    }
 #define PCL_GRAV2(IB, T, JT)                                                                                  \
-    pcl_k_gravity_x2<IB, T, JT><<<(unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), T, 0, st>>>(           \
-        (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
+    pcl_k_gravity_x2<IB, T, JT><<<dim3((unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), nsplit), T, 0, st>>>(  \
+        (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate, \
+        j_skip_begin, j_skip_end, part)
     switch (variant) {
         case 1: PCL_GRAV(4, 128); break;
         case 2: PCL_GRAV(2, 128); break;
@@ -269,6 +343,11 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
 #undef PCL_GRAV
 #undef PCL_GRAV2
     PCL_LAUNCHED(ctx);
+    if (part) {
+        unsigned grid = pcl_stream_grid(ctx, n_local, PCL_BLOCK, 8);
+        pcl_k_gravity_reduce<<<grid, PCL_BLOCK, 0, st>>>(part, nsplit, n_local, G, ax, ay, az, accumulate);
+        PCL_LAUNCHED(ctx);
+    }
     return 0;
 }
 

@@ -68,6 +68,7 @@ extern "C" int pcl_destroy(pcl_ctx *ctx) {
     pcl_hostpipe_destroy(ctx);
     if (ctx->kin_graph) cudaGraphExecDestroy(ctx->kin_graph);
     if (ctx->scan_buf) cudaFree(ctx->scan_buf);
+    if (ctx->grav_part) cudaFree(ctx->grav_part);
     free(ctx);
     return 0;
 }

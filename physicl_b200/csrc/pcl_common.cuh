@@ -42,6 +42,9 @@ struct pcl_ctx {
     // compaction scratch: per-block live counts / offsets
     uint32_t *scan_buf;
     size_t scan_cap;
+    // gravity: partial accelerations of the j splits
+    float *grav_part;
+    size_t grav_cap;
     // cached CUDA graph of a multi-step kinematics loop
     cudaGraphExec_t kin_graph;
     pcl_graph_key kin_key;

@@ -90,12 +90,11 @@ class GravityExchange:
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
             d.all_gather_into_tensor(self.all, posm)
-        # local block first (overlaps the gather)
-        ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0)
+        # local block first (overlaps the gather) ...
+        ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0,
+                 C.c_uint64(0), C.c_uint64(0))
         cur.wait_stream(self.side)
+        # ... then every other rank's block in ONE launch over the gathered array, own block skipped
         nl = self.n_local
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            blk = self.all[r * nl:(r + 1) * nl]
-            ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(blk), C.c_uint64(nl), *args, 1)
+        ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(self.all), C.c_uint64(self.world * nl), *args, 1,
+                 C.c_uint64(self.rank * nl), C.c_uint64((self.rank + 1) * nl))

@@ -92,7 +92,7 @@ class NewtonianGravityStep(physicl.Step):
         if "xchg" in s:
             s["xchg"].accelerations(ctx, st, posm, n, args)
         else:
-            ctx.call("pcl_gravity_accel", stream, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0)
+            ctx.call("pcl_gravity_accel", stream, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0, C.c_uint64(0), C.c_uint64(0))
         ctx.call("pcl_gravity_kick_drift", stream, C.c_uint64(n), p(posm), p(g.planes["vx"]), p(g.planes["vy"]),
                  p(g.planes["vz"]), p(acc[0]), p(acc[1]), p(acc[2]), C.c_float(float(sim.dt)),
                  p(g.planes["x"]), p(g.planes["y"]), p(g.planes["z"]))

@@ -409,7 +409,7 @@ def test_gravity_matches_float64_definition(ctx, n):
     acc = torch.zeros((3, n), dtype=torch.float32, device="cuda")
     p = lambda t: C.c_void_p(t.data_ptr())
     ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(G), C.c_float(eps2),
-             p(acc[0]), p(acc[1]), p(acc[2]), 0)
+             p(acc[0]), p(acc[1]), p(acc[2]), 0, C.c_uint64(0), C.c_uint64(0))
     torch.cuda.synchronize()
     pos32 = posm[:, :3].T.cpu().numpy().astype(np.float64)
     m32 = posm[:, 3].cpu().numpy().astype(np.float64)
@@ -431,15 +431,24 @@ def test_gravity_split_blocks_equal_whole(ctx):
     p = lambda t: C.c_void_p(t.data_ptr())
     whole = torch.zeros((3, n), dtype=torch.float32, device="cuda")
     ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(1.0), C.c_float(1e-4),
-             p(whole[0]), p(whole[1]), p(whole[2]), 0)
+             p(whole[0]), p(whole[1]), p(whole[2]), 0, C.c_uint64(0), C.c_uint64(0))
     parts = torch.zeros((3, n), dtype=torch.float32, device="cuda")
     for b in range(4):
         blk = posm[b * 512:(b + 1) * 512]
         ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(blk), C.c_uint64(512), C.c_float(1.0), C.c_float(1e-4),
-                 p(parts[0]), p(parts[1]), p(parts[2]), int(b > 0))
+                 p(parts[0]), p(parts[1]), p(parts[2]), int(b > 0), C.c_uint64(0), C.c_uint64(0))
+    # the sharded form: own block first, then the whole array with that block skipped (ragged skip range)
+    two = torch.zeros((3, n), dtype=torch.float32, device="cuda")
+    lo, hi = 700, 1801
+    own = posm[lo:hi].contiguous()
+    ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(own), C.c_uint64(hi - lo), C.c_float(1.0), C.c_float(1e-4),
+             p(two[0]), p(two[1]), p(two[2]), 0, C.c_uint64(0), C.c_uint64(0))
+    ctx.call("pcl_gravity_accel", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(1.0), C.c_float(1e-4),
+             p(two[0]), p(two[1]), p(two[2]), 1, C.c_uint64(lo), C.c_uint64(hi))
     torch.cuda.synchronize()
-    w, q = whole.cpu().numpy(), parts.cpu().numpy()
+    w, q, t2 = whole.cpu().numpy(), parts.cpu().numpy(), two.cpu().numpy()
     assert np.abs(w - q).max() <= 2e-5 * np.abs(w).max()
+    assert np.abs(w - t2).max() <= 2e-5 * np.abs(w).max()
 
 
 # ---------------------------------------------------------------------------------------------
