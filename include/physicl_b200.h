@@ -176,6 +176,16 @@ int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float 
 int pcl_tally(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_planes *planes,
               int64_t *tally_row);
 
+/* ScatterMeasureStep(measure_E=True) (light.py:380-402): for plane q, the (id, e = E/E0) of every live
+ * photon that crossed it this timestep, appended in arrival order to out_id/out_e[q*cap ...];
+ * counts_dev[q] = number of crossers (zeroed here; entries beyond cap are dropped, the count is not). */
+int pcl_plane_crossers(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const pcl_planes *planes,
+                       uint32_t *out_id, float *out_e, uint64_t *counts_dev, uint64_t cap);
+/* TracePathMeasureStep.run (light.py:447-460): r of every live particle written to slab[c*n_ids + id],
+ * c = 0,1,2; the caller pre-fills the slab with NaN ("object does not exist", light.py:435). */
+int pcl_trace_positions(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float *slab, uint64_t n_ids,
+                        uint32_t *nscat_by_id /* nullable: latest scatter count per id (light.py:459-460) */);
+
 /* Simulation.remove_obj for every retired photon (physicl/__init__.py:455-459): stable stream
  * compaction of live slots of `src` into `dst` (dst planes must not alias src; dst->id required).
  * n_live_dev: device uint64 receiving the live count. */

@@ -360,6 +360,9 @@ class Simulation(threading.Thread):
         for ordinal, s in enumerate(steps):  # distinct Philox keys for distinct stochastic steps
             if hasattr(s, "_salt"):
                 s._salt = ((ordinal + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        for s in steps:  # one-time set-up that must precede the first timestep (e.g. scatter counters)
+            if hasattr(s, "prepare"):
+                s.prepare(self)
         if not (self.fuse and self.cl_on):
             return steps
         from .fused import fuse_plan

@@ -78,6 +78,8 @@ _PROTOS = {
     "pcl_photon_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_void_p]),
     "pcl_photon_steps_pp": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Pingpong), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint32, C.c_uint32]),
     "pcl_tally": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Planes), C.c_void_p]),
+    "pcl_plane_crossers": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Planes), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "pcl_trace_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_void_p, C.c_uint64, C.c_void_p]),
     "pcl_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Soa), C.c_void_p]),
     "pcl_planck_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "pcl_gravity_accel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),

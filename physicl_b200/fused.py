@@ -177,6 +177,8 @@ class _FusedRow(int):
 
 
 def fuse_plan(steps):
+    if any(getattr(s, "needs_dr", False) for s in steps):
+        return list(steps)  # a step reads the dr planes (e.g. measure_E): kinematics must write them
     out, i = [], 0
     while i < len(steps):
         s = steps[i]

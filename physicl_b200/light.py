@@ -6,6 +6,7 @@ sm_100a kernels reached through the C ABI; see ``csrc/photon.cu``.
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 
 import numpy as np
@@ -306,8 +307,11 @@ class _DeviceMeasureStep(physicl.MeasureStep):
                 from .dist import all_reduce_rows
 
                 rows = all_reduce_rows(rows)
-            for (t, _, _, _), r in zip(pend, rows):
-                self._data.append(self._format(t, r))
+            for (t, _, grow, _), r in zip(pend, rows):
+                try:
+                    self._data.append(self._format(t, r, grow))
+                except TypeError:
+                    self._data.append(self._format(t, r))
         return self._data
 
     @data.setter
@@ -339,17 +343,21 @@ class _DeviceMeasureStep(physicl.MeasureStep):
 
 class ScatterMeasureStep(_DeviceMeasureStep):
     """light.py:361-404: row ``[t, N, crossings of each plane...]``; a plane is a 3-vector with NaN in
-    the two free coordinates; a crossing is ``r - dr <= loc <= r`` or ``r - dr >= loc >= r``."""
+    the two free coordinates; a crossing is ``r - dr <= loc <= r`` or ``r - dr >= loc >= r``.
+
+    ``measure_E=True`` (light.py:380-402) adds, after each plane's count, the list of the energies of
+    the photons that crossed it, in object order: ``[t, N, n_0, [E...], n_1, [E...], ...]`` (an object
+    array, as ragged rows have to be on current NumPy).  That form reads the ``dr`` planes, so a
+    pipeline containing it runs unfused."""
 
     def __init__(self, out_fn, measure_n=True, measure_locs=[], measure_E=False):
         super().__init__(out_fn)
         self.measure_locs = measure_locs
         self.measure_n = measure_n
         self.measure_E = measure_E
+        self.needs_dr = bool(measure_E)
         self._plane0 = 0  # first tally column of this step's planes (non-zero only inside a fused row)
-        if measure_E:
-            raise NotImplementedError("measure_E (energy lists of plane crossers, light.py:388-402) is not on the "
-                                      "device path yet (SURVEY.md section 8f rank 1)")
+        self._elists = {}  # global row -> [list of E per plane]
 
     def _planes(self):
         out = []
@@ -359,11 +367,48 @@ class ScatterMeasureStep(_DeviceMeasureStep):
             out.append((ax, float(loc[ax])))
         return out
 
-    def _format(self, t, r):
+    def run(self, sim):
+        super().run(sim)
+        if not self.measure_E or not self.measure_locs:
+            return
+        import torch
+
+        st = sim.device_store()
+        row = self._pending[-1][2]
+        pl = _capi.make_planes(self._planes())
+        lists = [[] for _ in self.measure_locs]
+        for kind, g in st.groups.items():
+            if g.n == 0 or kind != "photon":
+                continue  # only photons carry E (light.py:34); the reference would raise on other objects
+            st.sync_n(kind)
+            g.ensure("dx", "dy", "dz")
+            cap = g.n
+            ids = torch.empty(pl.count * cap, dtype=torch.int32, device=st.device)
+            es = torch.empty(pl.count * cap, dtype=torch.float32, device=st.device)
+            cnt = torch.zeros(pl.count, dtype=torch.int64, device=st.device)
+            soa = g.soa()
+            sim.cl_ctx.call("pcl_plane_crossers", st.stream(), C.byref(soa), C.byref(pl), C.c_void_p(ids.data_ptr()),
+                            C.c_void_p(es.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_uint64(cap))
+            counts = cnt.cpu().numpy()
+            for q in range(pl.count):
+                k = int(counts[q])
+                i = ids[q * cap:q * cap + k].cpu().numpy().view(np.uint32)
+                e = es[q * cap:q * cap + k].cpu().numpy().astype(np.float64) * g.e0
+                lists[q] = list(e[np.argsort(i, kind="stable")])  # object order = id order
+        self._elists[row] = lists
+
+    def _format(self, t, r, row=None):
         out = [t]
         if self.measure_n:
             out.append(int(r[_capi.T_ALIVE]))
-        out.extend(int(r[_capi.T_PLANE0 + self._plane0 + k]) for k in range(len(self.measure_locs)))
+        for k in range(len(self.measure_locs)):
+            out.append(int(r[_capi.T_PLANE0 + self._plane0 + k]))
+            if self.measure_E:
+                out.append(self._elists.get(row, [[]] * len(self.measure_locs))[k])
+        if self.measure_E:
+            arr = np.empty(len(out), dtype=object)
+            arr[:] = out
+            return arr
         return np.array(out)
 
 
@@ -383,9 +428,73 @@ class ScatterSignMeasureStep(_DeviceMeasureStep):
 
 
 class TracePathMeasureStep(physicl.MeasureStep):
-    """light.py:433-483 keeps a deep copy of every object's position every timestep: an O(N * steps)
-    host trace, out of scope for the device path.  Use
-    ``sim.store.snapshot()`` at the cadence you need, or ``track_nscat`` for scatter counts."""
+    """light.py:433-483: the position of every object at every timestep, plus (``trace_dv=True``) how
+    often its velocity changed, i.e. how often it scattered (light.py:459-460).
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError(self.__doc__)
+    Device form: each timestep one kernel scatters r by particle id into that step's slab of a
+    trajectory buffer (NaN where the object does not exist any more); ``terminate`` downloads the
+    slabs and lays ``data`` out exactly like the reference: first row ``["t", t_0, t_1, ...]``, then per
+    object ``[id_info, (freq,) r_0, r_1, ..., nan, nan, nan, ...]``.  The scatter count comes from the
+    per-photon ``nscat`` plane that every scatter kernel maintains."""
+
+    uses_device = True
+
+    def __init__(self, out_fn, trace_type=physicl.Object, id_info_fn=lambda x: str(type(x)), trace_dv=False):
+        super().__init__(out_fn)
+        self.trace_type = trace_type
+        self.id_info_fn = id_info_fn
+        self.trace_dv = trace_dv
+        self._slabs = []  # (kind, n_ids, device tensor [3*n_ids], column)
+        self._freq = {}  # kind -> int32 device tensor [n_ids]: latest scatter count per id
+
+    def prepare(self, sim):
+        """Called once before the first timestep: the scatter counters must exist before any scatter."""
+        if self.trace_dv:
+            st = sim.device_store()
+            for g in st.groups.values():
+                g.ensure("nscat", fill=0)
+
+    def run(self, sim):
+        import torch
+
+        st = sim.device_store()
+        for kind, g in st.groups.items():
+            st.sync_n(kind)
+            n_ids = g.n0 if hasattr(g, "n0") else g.n
+            if not hasattr(g, "n0"):
+                g.n0 = g.n  # ids are local indices of the group as ingested
+                n_ids = g.n0
+            slab = torch.full((3 * max(n_ids, 1),), float("nan"), dtype=torch.float32, device=st.device)
+            freq = None
+            if self.trace_dv:
+                if kind not in self._freq:
+                    self._freq[kind] = torch.zeros(max(n_ids, 1), dtype=torch.int32, device=st.device)
+                freq = C.c_void_p(self._freq[kind].data_ptr())
+            soa = g.soa()
+            sim.cl_ctx.call("pcl_trace_positions", st.stream(), C.byref(soa), C.c_void_p(slab.data_ptr()), C.c_uint64(n_ids), freq)
+            self._slabs.append((kind, n_ids, slab, len(sim.ts) - 1))
+
+    def terminate(self, sim):
+        st = sim.store
+        ts = list(sim.ts)
+        cols = len(ts)
+        dat = [["t"] + copy.deepcopy(ts)]
+        if st is not None:
+            for kind, g in st.groups.items():
+                n_ids = getattr(g, "n0", g.n)
+                steps = [(col, slab.cpu().numpy().reshape(3, -1)) for k, _, slab, col in self._slabs if k == kind]
+                freq = None
+                if self.trace_dv:
+                    freq = self._freq[kind].cpu().numpy()[:n_ids] if kind in self._freq else np.zeros(n_ids, np.int64)
+                cls = PhotonObject if kind == "photon" else physicl.Object
+                for i in range(n_ids):
+                    obj = g.host_objs[i] if g.host_objs is not None and not isinstance(g.host_objs, dict) else None
+                    row = [self.id_info_fn(obj) if obj is not None else str(cls)]
+                    if self.trace_dv:
+                        row.append(int(freq[i]))
+                    pos = [np.array(sl[:, i], np.float64) for _, sl in steps if not np.isnan(sl[0, i])]
+                    row.extend(pos)
+                    row.extend([np.nan, np.nan, np.nan] * (cols - len(pos)))  # light.py:480
+                    dat.append(row)
+        self.data = dat
+        super().terminate(sim)

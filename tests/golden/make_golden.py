@@ -273,6 +273,79 @@ def gen_kin(seed=15, N=64, nsteps=5):
     save("kin", N=N, nsteps=nsteps, seed=seed, r0=r0, v0=v0, dts=np.array(dts), **out)
 
 
+class _NumpyRagged:
+    """numpy >= 1.24 refuses ragged ``np.array([...])``; the reference's measure_E rows are ragged
+    (physicl/light.py:404).  Inside physicl.light only, fall back to an object array, which is what
+    older numpy produced."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def array(self, obj, *a, **k):
+        try:
+            return self._real.array(obj, *a, **k)
+        except ValueError:
+            out = self._real.empty(len(obj), dtype=object)
+            out[:] = obj
+            return out
+
+
+def gen_measure_E(seed=17, N=256, nsteps=5):
+    np.random.seed(seed)
+    T = 5778.0
+    E_min = float(physicl.light.E_from_wavelength(2500e-9))
+    E_max = float(physicl.light.E_from_wavelength(200e-9))
+    E = []
+    while len(E) < N:
+        e = physicl.light.planck_phot_distribution(E_min, E_max, T, bins=200)
+        if e is not None:
+            E.append(np.double(e))
+    E = np.array(E)
+    A, n, dt = np.double(5.1e-31 * (532e-9) ** 4), np.double(2.5e25), 1e-5
+    c = float(physicl.light.c)
+    planes = [[2.5 * c * dt, np.nan, np.nan], [np.nan, 0.2 * c * dt, np.nan]]
+    real_np = physicl.light.np
+    physicl.light.np = _NumpyRagged(real_np)
+    try:
+        with DrawLog() as log:
+            snap = Snapshot(log)
+            m = physicl.light.ScatterMeasureStep(None, True, [np.array(p, dtype=np.double) for p in planes], measure_E=True)
+            sim, launches = run_sim(photons(N, E), [physicl.newton.NewtonianKinematicsStep(),
+                                                    physicl.light.ScatterIsotropicStep(A=A, n=n, wavelength_dep_scattering=True),
+                                                    m, snap], nsteps, dt)
+    finally:
+        physicl.light.np = real_np
+    out = {}
+    for s, (st, row) in enumerate(zip(snap.rows, m.data)):
+        out["s%d_u" % s] = st["u"]
+        out["s%d_counts" % s] = np.array([row[1], row[2], row[4]], np.int64)
+        out["s%d_E0" % s] = np.array([float(x) for x in row[3]], np.float64)
+        out["s%d_E1" % s] = np.array([float(x) for x in row[5]], np.float64)
+    assert sum(len(out["s%d_E0" % s]) + len(out["s%d_E1" % s]) for s in range(nsteps)) > 0
+    save("measure_E", N=N, nsteps=nsteps, seed=seed, A=float(A), n=float(n), c=c, h=float(physicl.light.h), dt=dt, E=E,
+         planes=np.array(planes), **out)
+
+
+def gen_trace(seed=18, N=48, nsteps=6):
+    np.random.seed(seed)
+    A, n = np.double(0.002), np.double(0.001)
+    with DrawLog() as log:
+        snap = Snapshot(log)
+        tr = physicl.light.TracePathMeasureStep(None, trace_dv=True)
+        sim, launches = run_sim(photons(N), [physicl.newton.NewtonianKinematicsStep(),
+                                             physicl.light.ScatterIsotropicStep(A=A, n=n), tr, snap], nsteps, 0.001)
+    rows = tr.data
+    assert rows[0][0] == "t" and len(rows) == N + 1
+    freq = np.array([r[1] for r in rows[1:]], np.int64)
+    pos = np.array([[np.asarray(p, float) for p in r[2:2 + nsteps]] for r in rows[1:]])  # (N, steps, 3)
+    out = {"s%d_u" % s: st["u"] for s, st in enumerate(snap.rows)}
+    save("trace", N=N, nsteps=nsteps, seed=seed, A=float(A), n=float(n), c=float(physicl.light.c), dt=0.001,
+         ts=np.array([float(t) for t in rows[0][1:]]), freq=freq, pos=pos, id_info=np.array([str(r[0]) for r in rows[1:]]), **out)
+
+
 if __name__ == "__main__":
     gen_iso()
     gen_wave()
@@ -280,3 +353,5 @@ if __name__ == "__main__":
     gen_delete(seed=16, N=512, nsteps=3, reference_twin=True)
     gen_planck()
     gen_kin()
+    gen_measure_E()
+    gen_trace()

@@ -349,3 +349,95 @@ print(json.dumps({"c": c, "rows": np.array(m.data)[:, 1:].tolist()}))
     assert out[0]["c"] == 299792458.0 and abs(out[1]["c"] - 299792.458) < 1e-6
     a, b = np.array(out[0]["rows"]), np.array(out[1]["rows"])
     assert a.shape == b.shape and np.abs(a - b).max() <= 3  # float32 rounding may flip a decision or two
+
+
+# ---- list-producing measure steps, pinned to reference runs --------------
+def test_measure_E_lists_match_the_reference_run(golden):
+    """ScatterMeasureStep(measure_E=True) (light.py:380-402): same seed and host RNG stream as the
+    reference run behind tests/golden/measure_E.npz -> same counts and the same energy lists, in order."""
+    g = golden("measure_E")
+    N, c, dt = int(g["N"]), float(g["c"]), float(g["dt"])
+    np.random.seed(int(g["seed"]))
+    phys.light.last_planck_params = None
+    E_min, E_max = float(phys.light.E_from_wavelength(2500e-9)), float(phys.light.E_from_wavelength(200e-9))
+    E = []
+    while len(E) < N:  # the generator's loop: one np.random.rand() per call, None results skipped
+        e = phys.light.planck_phot_distribution(E_min, E_max, 5778.0, bins=200)
+        if e is not None:
+            E.append(np.double(e))
+    assert np.array_equal(np.array(E), g["E"])
+    x = phys.Simulation(cl_on=True, exit=lambda s: len(s.ts) >= int(g["nsteps"]))
+    for e in E:
+        x.add_obj(phys.light.PhotonObject(s=np.zeros(3), v=np.array([phys.light.c, 0, 0], dtype=np.double), E=e))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(g["A"]), n=np.double(g["n"]), wavelength_dep_scattering=True, rng="numpy"))
+    m = phys.light.ScatterMeasureStep(None, True, [np.array(p) for p in g["planes"]], measure_E=True)
+    x.add_step(3, m)
+    x.start()
+    x.join()
+    assert len(m.data) == int(g["nsteps"])
+    seen = 0
+    for s, row in enumerate(m.data):
+        assert row.dtype == object and len(row) == 6
+        assert [int(row[1]), int(row[2]), int(row[4])] == [int(q) for q in g["s%d_counts" % s]]
+        for got, want in ((row[3], g["s%d_E0" % s]), (row[5], g["s%d_E1" % s])):
+            assert len(got) == len(want)
+            if len(want):
+                np.testing.assert_allclose(np.array(got, float), want, rtol=2e-7)
+                seen += len(want)
+    assert seen > 0
+
+
+def test_trace_path_matches_the_reference_run(golden):
+    """TracePathMeasureStep(trace_dv=True) (light.py:433-483): positions of every photon at every
+    timestep and its scatter count, against the reference run behind tests/golden/trace.npz."""
+    g = golden("trace")
+    N, steps, c = int(g["N"]), int(g["nsteps"]), float(g["c"])
+    np.random.seed(int(g["seed"]))
+    x = phys.Simulation(cl_on=True, exit=lambda s: len(s.ts) >= steps)
+    for _ in range(N):
+        x.add_obj(phys.light.PhotonObject(**rand_ray()))
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(g["A"]), n=np.double(g["n"]), rng="numpy"))
+    tr = phys.light.TracePathMeasureStep(None, trace_dv=True)
+    x.add_step(3, tr)
+    x.start()
+    x.join()
+    rows = tr.data
+    assert rows[0][0] == "t" and np.allclose([float(t) for t in rows[0][1:]], g["ts"], rtol=1e-12)
+    assert len(rows) == N + 1
+    for i, row in enumerate(rows[1:]):
+        assert row[0].replace("physicl_b200", "physicl") == str(g["id_info"][i])
+        assert int(row[1]) == int(g["freq"][i])
+        pos = np.array(row[2:2 + steps], float)
+        assert np.abs(pos - g["pos"][i]).max() <= 1e-5 * c * 0.001 * steps
+    assert g["freq"].sum() > 0
+
+
+def test_trace_path_marks_retired_photons_and_keeps_their_counts():
+    n, steps = 2000, 10
+    x = phys.Simulation(cl_on=True, seed=3)
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x.add_particles(r, v)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+    x.add_step(3, phys.light.EscapeSphereStep(6.0e5))
+    tr = phys.light.TracePathMeasureStep(None, trace_dv=True)
+    x.add_step(4, tr)
+    x.run_steps(steps)
+    tr.terminate(x)
+    rows = tr.data[1:]
+    assert len(rows) == n
+    lengths = np.array([sum(1 for q in row[2:] if isinstance(q, np.ndarray)) for row in rows])
+    assert lengths.min() < steps and lengths.max() == steps  # some escaped, some survived
+    for row, k in zip(rows[:200], lengths[:200]):
+        assert len(row) == 2 + k + 3 * (steps - k)
+        if k:
+            assert np.linalg.norm(row[2 + k - 1]) < 6.0e5 + 3.0e5
+    freq = np.array([row[1] for row in rows])
+    assert freq.sum() > 0 and freq.max() <= steps

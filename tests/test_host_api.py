@@ -187,10 +187,7 @@ def test_device_steps_refuse_to_run_without_device():
 def test_out_of_scope_features_say_so():
     with pytest.raises(NotImplementedError):
         phys.light.ScatterIsotropicStep(variable_n=True, variable_n_fn="1.0")
-    with pytest.raises(NotImplementedError):
-        phys.light.ScatterMeasureStep(None, True, [], measure_E=True)
-    with pytest.raises(NotImplementedError):
-        phys.light.TracePathMeasureStep(None)
+    assert phys.light.ScatterMeasureStep(None, True, [], measure_E=True).needs_dr
 
 
 def test_fuse_plan_groups_the_canonical_pipeline():
