@@ -232,6 +232,46 @@ int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt,
 int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes);
 int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
 
+/* ---- run-time compiled kernels ------------------------------------------------------------------ */
+/* cl.Program(ctx, src).build() (physicl/__init__.py:597, light.py:160) for sm_100a: CUDA C++ text in,
+ * loaded module out (NVRTC: --gpu-architecture=sm_100a -fmad=false).  Needed where the reference's
+ * kernel only exists as run-time text: the variable_n expression (light.py:295-299) and user CLProgram
+ * kernels (physicl/__init__.py:583-597).  headers: in-memory includes (name, text).  The NVRTC log is
+ * the error text on failure. */
+typedef struct pcl_jit_module pcl_jit_module;
+typedef struct pcl_jit_kernel pcl_jit_kernel;
+int pcl_jit_build(pcl_ctx *ctx, const char *source, int n_headers, const char *const *header_names,
+                  const char *const *header_texts, pcl_jit_module **out);
+/* prog.<kernel_name> (physicl/__init__.py:656); the handle is owned by the module */
+int pcl_jit_get_kernel(pcl_ctx *ctx, pcl_jit_module *m, const char *kernel_name, pcl_jit_kernel **out);
+/* prog.<kernel>(queue, (n,), None, *args) (physicl/__init__.py:656): 1-D launch over n work items
+ * (256 threads per CTA, grid-stride); args[i] points at the i-th argument value. */
+int pcl_jit_launch(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kernel *k, uint64_t n, void **args);
+int pcl_jit_free(pcl_ctx *ctx, pcl_jit_module *m);
+/* compile only: needs neither a context nor a device; log receives the NVRTC log on failure */
+int pcl_jit_check(const char *source, int n_headers, const char *const *header_names,
+                  const char *const *header_texts, char *log, uint64_t log_cap, uint64_t *cubin_bytes);
+
+/* ScatterIsotropicStep(variable_n=True, variable_n_fn="<expression>") (light.py:295-299): the kernel
+ * computes pcoll = A * (expression) * norm [* (h c / E)^-4] in float64, where the name `A` is bound to
+ * the step's n and `n` to the step's A (light.py:287).  `k` is a kernel built from
+ * csrc/pcl_jit_photon.cuh with the expression spliced in: "pcl_jit_photon_step" for the fused
+ * timestep, "pcl_jit_scatter" for the stand-alone scatter on the dr planes. */
+typedef struct pcl_varn_params {
+    double kd;     /* the kernel's scalar A, times (E0/(h c))^4 with PCL_SCATTER_WAVELENGTH            */
+    double e0;     /* E[gid] = e * e0 for expressions that read the photon energy                     */
+    double a_slot; /* value of the kernel name `A` (= the step's n)                                   */
+    double n_slot; /* value of the kernel name `n` (= the step's A)                                   */
+} pcl_varn_params;
+/* nsteps fused timesteps, in place (as pcl_photon_steps); tally_table: int64[nsteps][PCL_TALLY_COLS] */
+int pcl_photon_steps_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kernel *k, const pcl_soa *p, float dt,
+                         const pcl_scatter_params *sp, const pcl_varn_params *vn, const pcl_rng *rng,
+                         float escape_r2, const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps);
+/* stand-alone scatter (as pcl_scatter) */
+int pcl_scatter_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kernel *k, const pcl_soa *p,
+                    const pcl_scatter_params *sp, const pcl_varn_params *vn, const pcl_rng *rng, int32_t *flags,
+                    int64_t *tally_row);
+
 /* ---- roofline denominators measured on the box --------------------------------------------- */
 /* FFMA-only and copy micro-kernels; results in TFLOP/s (2 flop per FMA) and GB/s (read+write). */
 int pcl_measure_fp32_peak(pcl_ctx *ctx, double *tflops);

@@ -41,6 +41,31 @@ def pcoll(dr, A, n, E=None, hc=None):
     return p
 
 
+def eval_density_expr(expr, r, E=None, dr=None, A=None, n=None):
+    """The user's OpenCL-C number-density expression of ``ScatterIsotropicStep(variable_n=True)``
+    (physicl/light.py:295-299) evaluated over all photons in float64: ``r0[gid]``, ``r1[gid]``, ``r2[gid]``
+    are the position components AFTER the kinematics step (the inputs are gathered when the scatter
+    step runs, physicl/__init__.py:606-629)."""
+    ns = {"pow": np.power, "exp": np.exp, "sqrt": np.sqrt, "log": np.log, "sin": np.sin, "cos": np.cos, "fabs": np.abs,
+          "gid": slice(None), "r0": r[0], "r1": r[1], "r2": r[2], "A": A, "n": n}
+    if E is not None:
+        ns["E"] = E
+    if dr is not None:
+        ns.update(d0=dr[0], d1=dr[1], d2=dr[2], norm=np.sqrt(dr[0] ** 2 + dr[1] ** 2 + dr[2] ** 2))
+    return eval(expr, {"__builtins__": {}}, ns) * np.ones(r.shape[1])
+
+
+def pcoll_variable_n(dr, r, expr, kernel_A, kernel_n=None, E=None, hc=None):
+    """physicl/light.py:299-306 with ``variable_n=True``: ``pcoll = A * (<expr>) * norm [* pow(hc/E, -4)]``
+    where the kernel name ``A`` holds the step's ``n`` (light.py:287 swaps the two constants), so the
+    step's cross-section does not enter (SURVEY.md appendix A #5)."""
+    norm = np.sqrt(dr[0] ** 2 + dr[1] ** 2 + dr[2] ** 2)
+    p = kernel_A * eval_density_expr(expr, r, E, dr, kernel_A, kernel_n) * norm
+    if E is not None:
+        p = p * (hc / E) ** -4.0
+    return p
+
+
 def scatter_sphere_kernel(dr, rtheta, rphi, rnd, A, n, c, E=None, hc=None):
     """physicl/light.py:303-315 kernel body.  Returns res (3, N) with res[0] = NaN where unaffected
     (res[1], res[2] are undefined there in the reference; NaN here)."""

@@ -44,6 +44,10 @@ class Rng(C.Structure):
                 ("u_theta", C.c_void_p), ("u_phi", C.c_void_p), ("u_rand", C.c_void_p)]
 
 
+class VarnParams(C.Structure):
+    _fields_ = [("kd", C.c_double), ("e0", C.c_double), ("a_slot", C.c_double), ("n_slot", C.c_double)]
+
+
 class Planes(C.Structure):
     _fields_ = [("count", C.c_uint32), ("axis", C.c_uint32 * MAX_PLANES), ("loc", C.c_float * MAX_PLANES)]
 
@@ -88,6 +92,13 @@ _PROTOS = {
     "pcl_photon_step_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pcl_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pcl_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pcl_jit_build": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]),
+    "pcl_jit_get_kernel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "pcl_jit_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "pcl_jit_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pcl_jit_check": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pcl_photon_steps_jit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(VarnParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint32]),
+    "pcl_scatter_jit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(ScatterParams), C.POINTER(VarnParams), C.POINTER(Rng), C.c_void_p, C.c_void_p]),
     "pcl_measure_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pcl_measure_fp32x2_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pcl_measure_copy_peak": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),

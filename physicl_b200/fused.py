@@ -44,6 +44,8 @@ class FusedPhotonStep(physicl.Step):
         self._planes = _capi.make_planes(planes)
         self._multi_plane = sum(1 for _, n in self._plane_slices if n) > 1
         self.retires = bool(escape or scatter.mode & _capi.SCATTER_DELETE)
+        # variable-density steps run a run-time compiled kernel (light.py:295-299), in place only
+        self.varn = bool(getattr(scatter, "variable_n", False))
         self.cadence = 4  # m: every m-th timestep compacts; adapted from lagged tally feedback
         self._fb = []  # pending feedback: (event, pinned int64[18], buffer index at enqueue time)
         self._fb_pool = []
@@ -102,7 +104,7 @@ class FusedPhotonStep(physicl.Step):
         the simulation times of the k steps, for the measure rows."""
         st = sim.device_store()
         g = st.group("photon")
-        if not self.retires:
+        if not self.retires or self.varn:
             st.sync_n("photon")
         if g.n == 0:
             return
@@ -112,7 +114,14 @@ class FusedPhotonStep(physicl.Step):
         r2 = self.escape.R ** 2 if self.escape else 0.0
         for nm in ("dx", "dy", "dz"):  # dr stays in registers; stale planes would mislead host readers
             g.planes.pop(nm, None)
-        if self.retires:
+        if self.varn:
+            soa = g.soa()
+            soa.dx = soa.dy = soa.dz = None
+            vn = self.scatter.varn_params(g)
+            sim.cl_ctx.call("pcl_photon_steps_jit", st.stream(), self.scatter.jit_kernel(sim.cl_ctx, "pcl_jit_photon_step"),
+                            C.byref(soa), C.c_float(float(dt)), C.byref(sp), C.byref(vn), C.byref(rng), C.c_float(r2),
+                            C.byref(self._planes), st.row_ptr(first), C.c_uint32(k))
+        elif self.retires:
             self._consume_feedback(sim, g)
             if getattr(sim, "compact_cadence", None):
                 self.cadence = int(sim.compact_cadence)
@@ -133,7 +142,7 @@ class FusedPhotonStep(physicl.Step):
         self._note(sim, first, k, ts)
         last = first + k - 1
         sim._mark_device_dirty(live_row=last)
-        if self.retires and sim.feedback_every and (sim.step_index + k) % sim.feedback_every == 0:
+        if self.retires and not self.varn and sim.feedback_every and (sim.step_index + k) % sim.feedback_every == 0:
             self._enqueue_feedback(st, g, last)
 
     # ---- one timestep --------------------------------------------------------------------------------
@@ -158,8 +167,14 @@ class FusedPhotonStep(physicl.Step):
             g.planes.pop(nm, None)
         soa = g.soa()
         r2 = self.escape.R ** 2 if self.escape else 0.0
-        sim.cl_ctx.call("pcl_photon_step", st.stream(), C.byref(soa), C.c_float(float(sim.dt)), C.byref(sp), C.byref(rng),
-                        C.c_float(r2), C.byref(self._planes), st.row_ptr())
+        if self.varn:
+            vn = self.scatter.varn_params(g)
+            sim.cl_ctx.call("pcl_photon_steps_jit", st.stream(), self.scatter.jit_kernel(sim.cl_ctx, "pcl_jit_photon_step"),
+                            C.byref(soa), C.c_float(float(sim.dt)), C.byref(sp), C.byref(vn), C.byref(rng), C.c_float(r2),
+                            C.byref(self._planes), st.row_ptr(), C.c_uint32(1))
+        else:
+            sim.cl_ctx.call("pcl_photon_step", st.stream(), C.byref(soa), C.c_float(float(sim.dt)), C.byref(sp), C.byref(rng),
+                            C.c_float(r2), C.byref(self._planes), st.row_ptr())
         st.synchronize()  # the injected uniform tensors must outlive the launch
         if self.retires:
             g.n_live = int(st.peek_row(row)[_capi.T_ALIVE])

@@ -175,6 +175,22 @@ class _ScatterBase(physicl.Step):
             mode |= _capi.SCATTER_WAVELENGTH
         return _capi.ScatterParams(k=k, c=float(c), mode=mode)
 
+    def varn_params(self, group):
+        """float64 constants of the variable-density kernel (light.py:287, :299-301)."""
+        a_slot, n_slot = float(self.n), float(self.A)  # the reference binds name "A" to n and "n" to A
+        kd = a_slot * (n_slot if getattr(self, "variable_n_apply_A", False) else 1.0)
+        if getattr(self, "wavelength_dep_scattering", False):
+            kd = kd * (group.e0 / (float(h) * float(c))) ** 4
+        return _capi.VarnParams(kd=kd, e0=float(group.e0), a_slot=a_slot, n_slot=n_slot)
+
+    def jit_kernel(self, ctx, name):
+        from . import jit
+
+        m = self._jit.get(id(ctx))
+        if m is None or m.ctx is not ctx:
+            m = self._jit[id(ctx)] = jit.Module(ctx, self._jit_source)
+        return m.kernel(name)
+
     def rng_params(self, sim, store, group):
         """Philox: nothing to upload.  'numpy': draw on the host in the reference's order
         (light.py:285: rtheta, rphi, rand per photon; light.py:235: rand only) and inject."""
@@ -209,7 +225,12 @@ class _ScatterBase(physicl.Step):
         rng, keep = self.rng_params(sim, st, g)
         row = st.new_row()
         soa = g.soa()
-        sim.cl_ctx.call("pcl_scatter", st.stream(), C.byref(soa), C.byref(sp), C.byref(rng), None, st.row_ptr())
+        if getattr(self, "variable_n", False):
+            vn = self.varn_params(g)
+            sim.cl_ctx.call("pcl_scatter_jit", st.stream(), self.jit_kernel(sim.cl_ctx, "pcl_jit_scatter"), C.byref(soa),
+                            C.byref(sp), C.byref(vn), C.byref(rng), None, st.row_ptr())
+        else:
+            sim.cl_ctx.call("pcl_scatter", st.stream(), C.byref(soa), C.byref(sp), C.byref(rng), None, st.row_ptr())
         if keep is not None:
             st.synchronize()
         sim._mark_device_dirty(live_row=row)
@@ -222,6 +243,13 @@ class ScatterIsotropicStep(_ScatterBase):
     multiplies the collision probability by ``(h c / E)^-4``.  New keyword arguments: ``rng``
     ('philox' in-kernel draws, or 'numpy' for the reference's host-side ``np.random`` stream) and ``seed``.
 
+    ``variable_n=True, variable_n_fn="<expression>"`` (light.py:295-299): the number density is the
+    user's OpenCL-C expression over ``r0[gid]``, ``r1[gid]``, ``r2[gid]`` (also ``E[gid]``, ``norm``),
+    evaluated in float64; the kernel is compiled at run time for sm_100a (``physicl_b200/jit.py``).  As in
+    the reference, that kernel computes ``A * (expression) * norm`` with the NAME ``A`` bound to this
+    step's ``n`` (light.py:287 swaps the two constants), so the step's ``A`` does not enter unless
+    ``variable_n_apply_A=True`` is passed (SURVEY.md appendix A #5).
+
     Note the direction law is the reference's: theta ~ U[0, 2 pi) polar, phi ~ U[0, pi) azimuth
     (light.py:285, :309-311), which is not uniform on the sphere (SURVEY.md appendix A #11)."""
 
@@ -231,9 +259,15 @@ class ScatterIsotropicStep(_ScatterBase):
         self.wavelength_dep_scattering = kwargs.get("wavelength_dep_scattering", False)
         self.variable_n = kwargs.get("variable_n", False)
         self.variable_n_fn = kwargs.get("variable_n_fn", None)
+        self.variable_n_apply_A = kwargs.get("variable_n_apply_A", False)
+        self._jit = {}  # ctx id -> jit.Module
         if self.variable_n:
-            raise NotImplementedError("variable_n splices a user OpenCL-C expression into the kernel (light.py:295-299); "
-                                      "it is outside this backend's hand-written kernels (SURVEY.md section 8f)")
+            from . import jit
+
+            # built when the step is created, so that a bad expression fails here and not mid-run
+            self._jit_source = jit.photon_source(self.variable_n_fn, self.wavelength_dep_scattering)
+            if kwargs.get("check_expression", True):
+                jit.check(self._jit_source)
         self._init_rng(kwargs.get("rng", "philox"), kwargs.get("seed", None))
 
 

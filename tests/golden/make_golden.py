@@ -346,6 +346,56 @@ def gen_trace(seed=18, N=48, nsteps=6):
          ts=np.array([float(t) for t in rows[0][1:]]), freq=freq, pos=pos, id_info=np.array([str(r[0]) for r in rows[1:]]), **out)
 
 
+def eval_cl_expr(expr, **arrays):
+    """The user's OpenCL-C density expression evaluated with NumPy in float64 (gid = every photon)."""
+    ns = {"pow": np.power, "exp": np.exp, "sqrt": np.sqrt, "log": np.log, "sin": np.sin, "cos": np.cos, "fabs": np.abs,
+          "gid": slice(None)}
+    ns.update(arrays)
+    return eval(expr, {"__builtins__": {}}, ns)
+
+
+def gen_varn(name, expr, wave, n_kwarg, A_kwarg, dt, seed, N=512, nsteps=5):
+    """ScatterIsotropicStep(variable_n=True) (light.py:295-299): the reference splices `expr` into its
+    kernel; the generated kernel text and scalar bindings are stored next to the outputs."""
+    np.random.seed(seed)
+    T = 5778.0
+    E_min = float(physicl.light.E_from_wavelength(2500e-9))
+    E_max = float(physicl.light.E_from_wavelength(200e-9))
+    E = []
+    while len(E) < N:
+        e = physicl.light.planck_phot_distribution(E_min, E_max, T, bins=200)
+        if e is not None:
+            E.append(np.double(e))
+    E = np.array(E)
+    with DrawLog() as log:
+        snap = Snapshot(log)
+        sign = physicl.light.ScatterSignMeasureStep(None, True)
+        step = physicl.light.ScatterIsotropicStep(A=A_kwarg, n=n_kwarg, wavelength_dep_scattering=wave, variable_n=True,
+                                                  variable_n_fn=expr)
+        sim, launches = run_sim(photons(N, E), [physicl.newton.NewtonianKinematicsStep(), step, sign, snap], nsteps, dt)
+    hc = float(physicl.light.h) * float(physicl.light.c)
+    mm, fracs = 1.0, []
+    for la in launches:
+        b = la["before"]
+        norm = np.sqrt(b["d0"] ** 2 + b["d1"] ** 2 + b["d2"] ** 2)
+        dens = eval_cl_expr(expr, r0=b["r0"], r1=b["r1"], r2=b["r2"])
+        pc = la["scalars"]["A"] * dens * norm
+        if wave:
+            pc = pc * (hc / b["E"]) ** -4
+        hit = pc >= b["rand"]
+        assert np.array_equal(hit, ~np.isnan(la["after"]["res0"]))  # the restated law is the reference's
+        mm = min(mm, float(np.min(np.abs(pc - b["rand"]) / np.maximum(pc, 1e-300))))
+        fracs.append(hit.mean())
+    assert mm > 1e-4, mm
+    assert 0.02 < np.mean(fracs) < 0.9, fracs
+    keys = ["d0", "d1", "d2", "r0", "r1", "r2", "rtheta", "rphi", "rand", "res0", "res1", "res2"] + (["E"] if wave else [])
+    out = pack_steps(snap.rows, launches, keys)
+    save(name, N=N, nsteps=nsteps, seed=seed, A=float(A_kwarg), n=float(n_kwarg), c=float(physicl.light.c),
+         h=float(physicl.light.h), dt=dt, E=E, wave=bool(wave), expr=np.array(expr), sign_rows=np.array(sign.data), min_margin=mm,
+         kernel_A=launches[0]["scalars"]["A"], kernel_n=launches[0]["scalars"]["n"], scattered_fraction=np.array(fracs),
+         kernel_src=np.array(step.prog.kernel_code), **out)
+
+
 if __name__ == "__main__":
     gen_iso()
     gen_wave()
@@ -355,3 +405,9 @@ if __name__ == "__main__":
     gen_kin()
     gen_measure_E()
     gen_trace()
+    # examples/presentation_example.ipynb cell 0 (radial atmosphere) and presentation_example_2.ipynb cell 0 (plane
+    # atmosphere) forms, scaled so that some but not all photons scatter per step
+    gen_varn("varn", "{} * exp(-1 * ({} - {})/({}))".format(6.0e26, "sqrt(pow(r0[gid], 2) + pow(r1[gid], 2) + pow(r2[gid], 2))",
+                                                            1000.0, 8000.0),
+             True, np.double(5.1e-31 * (532e-9) ** 4), np.double(123.0), 1e-5, seed=19)
+    gen_varn("varn_z", "{} * exp(r2[gid] / {})".format(1.0e-3, 2.0e6), False, np.double(1.0e-3), np.double(7.0), 1e-3, seed=20)

@@ -184,9 +184,11 @@ def test_device_steps_refuse_to_run_without_device():
         s.join()
 
 
-def test_out_of_scope_features_say_so():
-    with pytest.raises(NotImplementedError):
-        phys.light.ScatterIsotropicStep(variable_n=True, variable_n_fn="1.0")
+def test_variable_n_and_measure_E_are_in_scope():
+    st = phys.light.ScatterIsotropicStep(variable_n=True, variable_n_fn="1.0", check_expression=False)
+    assert st.variable_n and "PCL_USER_N_EXPR 1.0" in st._jit_source
+    plan = fused.fuse_plan([phys.newton.NewtonianKinematicsStep(), st])
+    assert isinstance(plan[0], fused.FusedPhotonStep) and plan[0].varn
     assert phys.light.ScatterMeasureStep(None, True, [], measure_E=True).needs_dr
 
 
