@@ -173,7 +173,7 @@ class Simulation(threading.Thread):
         self.seed = 0
         self.fuse = True
         self.shard = False
-        self.feedback_every = 4  # timesteps per device chunk / between asynchronous tally read-backs
+        self.feedback_every = 8  # timesteps per device chunk (one C-ABI call, one asynchronous tally read-back)
         self.compact_cadence = None  # every m-th timestep retires-and-compacts; None = adaptive
         for attr, val in kwargs.items():
             setattr(self, attr, val)
@@ -409,13 +409,12 @@ class Simulation(threading.Thread):
             self.t, self.dt = 0, 0
         nsteps = int(nsteps)
         # bulk form: [UpdateTimeStep, fused photon step] with a constant dt goes to the device in
-        # chunks of up to feedback_every timesteps per C-ABI call
+        # chunks of about feedback_every timesteps per C-ABI call (a whole number of compaction periods)
         if (len(plan) == 2 and type(plan[0]) is UpdateTimeStep and hasattr(plan[1], "run_many")
                 and plan[1].can_run_many(self)):
             upd, fused = plan
             while nsteps > 0:
-                room = self.feedback_every - self.step_index % self.feedback_every if self.feedback_every else 64
-                k = min(nsteps, room, 256)
+                k = min(nsteps, fused.chunk_steps(self), 256)
                 dts, ts = [], []
                 for _ in range(k):
                     upd.run(self)

@@ -9,7 +9,7 @@
 
 int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                         int64_t *tally_row, uint64_t *n_out);
+                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps);
 
 #define PIPE_SLOTS 4
 #define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
@@ -117,7 +117,7 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
                 r.u_phi = b[10];
             }
         }
-        rc = pcl_photon_step_impl(ctx, st, &d, nullptr, dt, sp, &r, escape_r2, planes, hp->tally_dev, nullptr);
+        rc = pcl_photon_step_impl(ctx, st, &d, nullptr, dt, sp, &r, escape_r2, planes, hp->tally_dev, nullptr, 1);
         if (rc) return rc;
         float *dst[6] = {host->x, host->y, host->z, host->vx, host->vy, host->vz};
         for (int q = 0; q < 6; ++q)
@@ -196,7 +196,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
         if (wave) { src.e = in[6]; dst.e = ou[6]; }
         src.id = (uint32_t *)in[7]; dst.id = (uint32_t *)ou[7];
         if (host->nscat) { src.nscat = (uint32_t *)in[8]; dst.nscat = (uint32_t *)ou[8]; }
-        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s);
+        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, 1);
         if (rc) return rc;
         PCL_CUDA(ctx, cudaMemcpyAsync(hp->cnt_pinned + s, hp->cnt_dev + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (c + 1 >= PIPE_SLOTS) {  // oldest chunk in flight: its slot is needed next

@@ -19,6 +19,8 @@
 #define PCL_PHOTON_MINB 3
 #endif
 #define PCL_WARPS (PCL_BLOCK / 32)
+// most timesteps one photon launch advances in registers (pcl_k_photon_multi)
+#define PCL_FUSE_MAX 8
 
 struct pcl_graph_key {
     pcl_soa p;

@@ -92,12 +92,15 @@ __device__ __forceinline__ uint32_t pcl_scatter_one(bool live, float dx, float d
     return hit ? F_SCATTERED : 0u;
 }
 
-__device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut, float &up, float &ur) {
-    uint4 r = pcl_philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), K.step, 0u),
+__device__ __forceinline__ void pcl_draw_at(const StepK &K, uint32_t step, uint64_t gid, float &ut, float &up, float &ur) {
+    uint4 r = pcl_philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), step, 0u),
                                 make_uint2(K.seed_lo, K.seed_hi));
     ut = pcl_u01(r.x);
     up = pcl_u01(r.y);
     ur = pcl_u01(r.z);
+}
+__device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut, float &up, float &ur) {
+    pcl_draw_at(K, K.step, gid, ut, up, ur);
 }
 
 template <int NC>

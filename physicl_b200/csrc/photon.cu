@@ -224,24 +224,42 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused photon step with retirement folded in: reads the live photons of `s`, writes the survivors
-// densely into `d` (ping-pong partner), so the next step touches live photons only and a warp never
-// spends bandwidth or issue slots on retired ones.  Survivors of a 1024-slot tile keep their order
-// (ballot-free: 4-bit masks, shuffle scan, one atomic range reservation per tile); tiles land in
-// reservation order, which is why ids travel with the photons (RNG counter, identity).
-// Traffic per live photon-step: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
+// Several timesteps per HBM round trip.  Photons do not interact, so a thread can keep its four
+// photons in registers and advance them `nsteps` timesteps (kinematics -> scatter -> escape -> tallies,
+// a fresh Philox block per photon and timestep, one tally row per timestep) before anything goes
+// back to HBM: the traffic per photon-step drops by nsteps and the kernel becomes bound by the
+// instruction issue rate instead of by DRAM.  Results are bit-identical to nsteps single-step launches.
+//
+// COMPACT: retirement folded in.  The survivors of the last timestep are written densely into `d`
+// (the ping-pong partner), so the next launch touches live photons only and a warp never spends
+// bandwidth or issue slots on photons retired in earlier launches.  Survivors of a 1024-slot tile
+// keep their order (4-bit keep masks, shuffle scan, one atomic range reservation per tile); tiles land
+// in reservation order, which is why ids travel with the photons (RNG counter, identity).
+// Traffic per live photon and launch: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
+// !COMPACT: in place; r is always written, v and nscat only by groups in which a photon scattered.
 // ---------------------------------------------------------------------------------------------
-template <bool WAVE, bool DEL, bool INJ, bool PL>
+template <int NC>
+__device__ __forceinline__ void pcl_tally_to_shared(const uint32_t (&cnt)[NC], unsigned int *acc, uint32_t nplanes) {
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        if (q < C_PLANE0 + (int)nplanes) {
+            unsigned int w = __reduce_add_sync(0xffffffffu, cnt[q]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&acc[q], w);
+        }
+    }
+}
+
+template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
 __global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
-pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned long long *n_out) {
+pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
     constexpr int NC = PL ? C_N : C_PLANE0;
-    constexpr int NST = WAVE ? 9 : 8;  // staged planes: x y z vx vy vz id nscat [e]
-    __shared__ float s_stage[NST][PCL_BLOCK * 4];
+    constexpr int NST = COMPACT ? (WAVE ? 9 : 8) : 1;  // staged planes: x y z vx vy vz id nscat [e]
+    __shared__ float s_stage[NST][COMPACT ? PCL_BLOCK * 4 : 1];
     __shared__ uint32_t s_warp[PCL_WARPS];
     __shared__ unsigned long long s_base;
-    uint32_t cnt[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    __shared__ unsigned int s_acc[PCL_FUSE_MAX][C_N];
+    for (uint32_t q = threadIdx.x; q < PCL_FUSE_MAX * C_N; q += PCL_BLOCK) (&s_acc[0][0])[q] = 0u;
+    __syncthreads();
     const uint64_t n = pcl_valid_slots(s);
     const uint64_t ntiles = (n + PCL_BLOCK * 4 - 1) / (PCL_BLOCK * 4);
     const bool has_id = s.id != nullptr;
@@ -253,7 +271,8 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
         uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
         float4 ut4, up4, ur4;
         const float qnan = __int_as_float(0x7fc00000);
-        if (i + 3 < n) {
+        const bool full = i + 3 < n;
+        if (full) {
             x = pcl_ld4(s.x + i), y = pcl_ld4(s.y + i), z = pcl_ld4(s.z + i);
             vx = pcl_ld4(s.vx + i), vy = pcl_ld4(s.vy + i), vz = pcl_ld4(s.vz + i);
             if (WAVE) e = pcl_ld4(s.e + i);
@@ -288,23 +307,65 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
                 }
             }
         }
+        uint32_t any_scat = 0u;
+        for (uint32_t st = 0; st < nsteps; ++st) {
+            // all four photons of every lane of this warp retired: nothing left to do for the warp
+            const bool alive = (x.x == x.x) || (x.y == x.y) || (x.z == x.z) || (x.w == x.w);
+            if (!__any_sync(0xffffffffu, alive)) break;
+            uint32_t cnt[NC];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+            float ut[4], up[4], ur[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {  // four independent Philox chains: the compiler interleaves them
+                if (INJ) {
+                    ut[l] = pcl_f4(ut4, l);
+                    up[l] = pcl_f4(up4, l);
+                    ur[l] = pcl_f4(ur4, l);
+                } else {
+                    pcl_draw_at(K, K.step + st, s.id_base + (uint64_t)pcl_u4(id, l), ut[l], up[l], ur[l]);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                       pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut[l], up[l], ur[l], cnt);
+                const bool sc = !DEL && (f & F_SCATTERED);
+                any_scat |= sc ? 1u : 0u;
+                pcl_u4(nsc, l) += sc ? 1u : 0u;
+            }
+            pcl_tally_to_shared(cnt, s_acc[st], K.nplanes);
+        }
+        if (!COMPACT) {
+            if (full) {
+                pcl_st4(s.x + i, x);
+                pcl_st4(s.y + i, y);
+                pcl_st4(s.z + i, z);
+                if (any_scat) {
+                    pcl_st4(s.vx + i, vx);
+                    pcl_st4(s.vy + i, vy);
+                    pcl_st4(s.vz + i, vz);
+                    if (s.nscat) pcl_st4u(s.nscat + i, nsc);
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    if (i + l < n) {
+                        s.x[i + l] = pcl_f4(x, l);
+                        s.y[i + l] = pcl_f4(y, l);
+                        s.z[i + l] = pcl_f4(z, l);
+                        s.vx[i + l] = pcl_f4(vx, l);
+                        s.vy[i + l] = pcl_f4(vy, l);
+                        s.vz[i + l] = pcl_f4(vz, l);
+                        if (s.nscat) s.nscat[i + l] = pcl_u4(nsc, l);
+                    }
+                }
+            }
+            continue;
+        }
         uint32_t keep = 0u;
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            if (pcl_f4(x, l) != pcl_f4(x, l)) continue;
-            float ut, up, ur;
-            if (INJ) {
-                ut = pcl_f4(ut4, l);
-                up = pcl_f4(up4, l);
-                ur = pcl_f4(ur4, l);
-            } else {
-                pcl_draw(K, s.id_base + (uint64_t)pcl_u4(id, l), ut, up, ur);
-            }
-            uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                   pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut, up, ur, cnt);
-            pcl_u4(nsc, l) += (!DEL && (f & F_SCATTERED)) ? 1u : 0u;
-            keep |= (f & (F_ABSORBED | F_ESCAPED)) ? 0u : (1u << l);
-        }
+        for (int l = 0; l < 4; ++l) keep |= (pcl_f4(x, l) == pcl_f4(x, l)) ? (1u << l) : 0u;
         // tile-local rank of this thread's first survivor: shuffle scan inside the warp, warp totals
         // through shared memory
         const uint32_t c = __popc(keep);
@@ -357,7 +418,12 @@ pcl_k_photon_step_compact(pcl_soa s, pcl_soa d, StepK K, int64_t *row, unsigned 
         }
         __syncthreads();  // the stage and s_warp are rewritten by the next tile
     }
-    pcl_flush_tally(cnt, row, K.nplanes);
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < nsteps * C_N; q += PCL_BLOCK) {
+        const unsigned int v = (&s_acc[0][0])[q];
+        // register column -> PCL_T_* column (identical numbering by construction); row st = rows + st*COLS
+        if (v) atomicAdd((unsigned long long *)&rows[q], (unsigned long long)v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,9 +563,21 @@ int pcl_fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *s
     return 0;
 }
 
+// timesteps per launch for multi-step runs: PCL_PHOTON_FUSE=1 restores one launch per timestep
+static uint32_t photon_fuse_max() {
+    static int fuse = -1;
+    if (fuse < 0) {
+        const char *e = getenv("PCL_PHOTON_FUSE");
+        fuse = e ? atoi(e) : PCL_FUSE_MAX;
+        if (fuse < 1) fuse = 1;
+        if (fuse > PCL_FUSE_MAX) fuse = PCL_FUSE_MAX;
+    }
+    return (uint32_t)fuse;
+}
+
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
-                            int64_t *row, uint64_t *n_out) {
+                            int64_t *row, uint64_t *n_out, uint32_t nsteps) {
     const bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) && pcl_aligned16(p.vx) &&
                          pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
                          pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
@@ -508,8 +586,15 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         PCL_REQUIRE(ctx, aligned, "the compacting step needs 16-byte aligned planes");
         PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
-        pcl_k_photon_step_compact<WAVE, DEL, INJ, PL><<<grid, PCL_BLOCK, 0, st>>>(p, *dst, K, row,
-                                                                                     (unsigned long long *)n_out);
+        pcl_k_photon_multi<WAVE, DEL, INJ, PL, true><<<grid, PCL_BLOCK, 0, st>>>(p, *dst, K, row, (unsigned long long *)n_out,
+                                                                                  nsteps);
+        PCL_LAUNCHED(ctx);
+        return 0;
+    }
+    if (nsteps > 1) {  // several timesteps per HBM round trip, in place
+        PCL_REQUIRE(ctx, aligned, "multi-step launches need 16-byte aligned planes");
+        unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
+        pcl_k_photon_multi<WAVE, DEL, INJ, PL, false><<<grid, PCL_BLOCK, 0, st>>>(p, p, K, row, nullptr, nsteps);
         PCL_LAUNCHED(ctx);
         return 0;
     }
@@ -543,23 +628,23 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
 
 template <bool WAVE, bool DEL, bool INJ>
 static int launch_photon(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
-                         int64_t *row, uint64_t *n_out) {
-    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, dst, K, row, n_out)
-                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, dst, K, row, n_out);
+                         int64_t *row, uint64_t *n_out, uint32_t nsteps) {
+    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, dst, K, row, n_out, nsteps)
+                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, dst, K, row, n_out, nsteps);
 }
 
 static int photon_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, const StepK &K,
-                           uint32_t mode, int64_t *row, uint64_t *n_out) {
+                           uint32_t mode, int64_t *row, uint64_t *n_out, uint32_t nsteps) {
     const bool wave = mode & PCL_SCATTER_WAVELENGTH, del = mode & PCL_SCATTER_DELETE, inj = K.u_rand != nullptr;
     switch ((wave ? 4 : 0) | (del ? 2 : 0) | (inj ? 1 : 0)) {
-        case 0: return launch_photon<false, false, false>(ctx, st, *p, dst, K, row, n_out);
-        case 1: return launch_photon<false, false, true>(ctx, st, *p, dst, K, row, n_out);
-        case 2: return launch_photon<false, true, false>(ctx, st, *p, dst, K, row, n_out);
-        case 3: return launch_photon<false, true, true>(ctx, st, *p, dst, K, row, n_out);
-        case 4: return launch_photon<true, false, false>(ctx, st, *p, dst, K, row, n_out);
-        case 5: return launch_photon<true, false, true>(ctx, st, *p, dst, K, row, n_out);
-        case 6: return launch_photon<true, true, false>(ctx, st, *p, dst, K, row, n_out);
-        default: return launch_photon<true, true, true>(ctx, st, *p, dst, K, row, n_out);
+        case 0: return launch_photon<false, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 1: return launch_photon<false, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 2: return launch_photon<false, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 3: return launch_photon<false, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 4: return launch_photon<true, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 5: return launch_photon<true, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 6: return launch_photon<true, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        default: return launch_photon<true, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
     }
 }
 
@@ -571,11 +656,15 @@ static int check_photon_view(pcl_ctx *ctx, const pcl_soa *p, const pcl_scatter_p
     return 0;
 }
 
+// nsteps timesteps in one launch (1 <= nsteps <= PCL_FUSE_MAX; tally_row: nsteps consecutive rows).
+// dst: write the survivors of the last timestep densely into *dst (count in *n_out) instead of in place.
 int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                         int64_t *tally_row, uint64_t *n_out) {
+                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps) {
     int rc = check_photon_view(ctx, p, sp);
     if (rc) return rc;
+    PCL_REQUIRE(ctx, nsteps >= 1 && nsteps <= PCL_FUSE_MAX, "bad number of timesteps per launch");
+    PCL_REQUIRE(ctx, nsteps == 1 || !(rng && rng->u_rand), "injected uniforms are per timestep");
     PCL_REQUIRE(ctx, tally_row != nullptr, "tally_row is required");
     if (dst) {
         PCL_REQUIRE(ctx, n_out != nullptr, "n_out_dev is required");
@@ -593,14 +682,14 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
     StepK K;
     rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
     if (rc) return rc;
-    return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out);
+    return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out, nsteps);
 }
 
 extern "C" int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                                const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                                const pcl_planes *planes, int64_t *tally_row) {
     PCL_ENTER(ctx);
-    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, nullptr, dt, sp, rng, escape_r2, planes, tally_row, nullptr);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, nullptr, dt, sp, rng, escape_r2, planes, tally_row, nullptr, 1);
 }
 
 extern "C" int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_soa *dst, float dt,
@@ -608,7 +697,7 @@ extern "C" int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl
                                        const pcl_planes *planes, int64_t *tally_row, uint64_t *n_out_dev) {
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, dst != nullptr, "dst is required");
-    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, src, dst, dt, sp, rng, escape_r2, planes, tally_row, n_out_dev);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, src, dst, dt, sp, rng, escape_r2, planes, tally_row, n_out_dev, 1);
 }
 
 extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float dt,
@@ -622,18 +711,30 @@ extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong 
     cudaStream_t st = (cudaStream_t)stream;
     PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
     pcl_rng r = *rng;
-    for (uint32_t s = 0; s < nsteps; ++s) {
+    const uint32_t fuse = photon_fuse_max();
+    for (uint32_t s = 0; s < nsteps;) {
         r.step = rng->step + s;
         int64_t *row = tally_table + (size_t)s * PCL_TALLY_COLS;
         pcl_soa src = pp->buf[pp->cur];
         src.n_dev = pp->n_dev + pp->cur;
         if (!((pp->id_valid >> pp->cur) & 1u)) src.id = nullptr;
-        const bool compacting = compact_every && ((uint64_t)r.step + 1) % compact_every == 0;
+        // this launch advances up to `fuse` timesteps in registers; it ends at the next compaction
+        // boundary (every compact_every-th timestep, counted on the global step index), where the
+        // survivors are written densely into the partner buffer
+        uint32_t run = nsteps - s < fuse ? nsteps - s : fuse;
+        bool compacting = false;
+        if (compact_every) {
+            const uint64_t to_boundary = compact_every - ((uint64_t)r.step % compact_every);  // 1 .. compact_every
+            if (to_boundary <= run) {
+                run = (uint32_t)to_boundary;
+                compacting = true;
+            }
+        }
         int rc;
         if (compacting) {
             pcl_soa dst = pp->buf[pp->cur ^ 1];
             dst.n = src.n;
-            rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, &r, escape_r2, planes, row, pp->n_dev + (pp->cur ^ 1));
+            rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, &r, escape_r2, planes, row, pp->n_dev + (pp->cur ^ 1), run);
             if (rc == 0) {
                 pp->buf[pp->cur ^ 1].n = src.n;  // upper bound; the exact count is n_dev[cur]
                 pp->buf[pp->cur ^ 1].id_base = src.id_base;
@@ -641,9 +742,10 @@ extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong 
                 pp->id_valid |= 1u << pp->cur;
             }
         } else {
-            rc = pcl_photon_step_impl(ctx, st, &src, nullptr, dt, sp, &r, escape_r2, planes, row, nullptr);
+            rc = pcl_photon_step_impl(ctx, st, &src, nullptr, dt, sp, &r, escape_r2, planes, row, nullptr, run);
         }
         if (rc) return rc;
+        s += run;
     }
     return 0;
 }
@@ -658,11 +760,14 @@ extern "C" int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p
     cudaStream_t st = (cudaStream_t)stream;
     PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
     pcl_rng r = *rng;
-    for (uint32_t s = 0; s < nsteps; ++s) {
+    const uint32_t fuse = photon_fuse_max();
+    for (uint32_t s = 0; s < nsteps;) {
+        const uint32_t run = nsteps - s < fuse ? nsteps - s : fuse;
         r.step = rng->step + s;
         int rc = pcl_photon_step_impl(ctx, st, p, nullptr, dt, sp, &r, escape_r2, planes,
-                                      tally_table + (size_t)s * PCL_TALLY_COLS, nullptr);
+                                      tally_table + (size_t)s * PCL_TALLY_COLS, nullptr, run);
         if (rc) return rc;
+        s += run;
     }
     return 0;
 }

@@ -7,14 +7,21 @@ which issues the fused photon kernel (kinematics + scatter + escape + sign/plane
 round trip, dr kept in registers) and hands the tally row to the member measure steps.  Any other
 step order runs unfused, kernel by kernel, in the user's order.
 
+Several timesteps per HBM round trip.  In the bulk form (``Simulation.run_steps``) a launch keeps its
+photons in registers for up to 8 timesteps (``pcl_k_photon_multi``; results identical bit for bit to
+one launch per timestep), so the state crosses HBM once per launch and the kernel is bound by the
+integer/FP32 pipes, not by DRAM.
+
 Retirement policy.  When the pipeline can retire photons (delete scattering, escape sphere) the
-step runs on the store's ping-pong plane sets through ``pcl_photon_steps_pp``: every m-th timestep is
-a retire-and-compact step, the others update in place.  In-place steps move ~44 B per SLOT, a
-compacting step ~56 B per live photon, so with a death rate d per step the traffic per live
-photon-step is about 44 + 12/m + 22 m d: minimal at m = sqrt(0.545 / d).  d comes from the tally
-rows with a lag: after every chunk of ``sim.feedback_every`` timesteps the last row and the device
-slot counters are copied to pinned host memory asynchronously, and the host reads them one or two
-chunks later (it only ever waits on work the GPU has long finished), so the stepping loop has no
+step runs on the store's ping-pong plane sets through ``pcl_photon_steps_pp``: a launch covers m
+timesteps and writes the survivors of the last one densely into the partner buffer.  Photons that
+die inside a launch idle in their lanes until it ends (a fraction ~ d (m-1)/2 of the issue slots for
+a death rate d per step) while the load/compaction phase of a launch costs about a third of a
+timestep's instructions: the cost per live photon-step is ~ 1 + d (m-1)/2 + 0.32/m, minimal at
+m = sqrt(0.645 / d), capped at the 8 timesteps a launch can hold.  d comes from the tally rows with a
+lag: after every chunk (one C-ABI call, about ``sim.feedback_every`` timesteps) the last row and the
+device slot counters are copied to pinned host memory asynchronously, and the host reads them one or
+two chunks later (it only ever waits on work the GPU has long finished), so the stepping loop has no
 blocking host<->device round trip.
 """
 from __future__ import annotations
@@ -66,10 +73,23 @@ class FusedPhotonStep(physicl.Step):
             for m, sl in zip(self.measures, self._plane_slices):
                 m._note_row(sim, _FusedRow(row, sl), t=None if ts is None else ts[i])
 
+    def chunk_steps(self, sim):
+        """Timesteps per C-ABI call: a whole number of compaction periods close to sim.feedback_every."""
+        fe = int(sim.feedback_every) if sim.feedback_every else 8
+        if not self.retires or self.varn:
+            return max(fe, 1)
+        m = int(sim.compact_cadence) if getattr(sim, "compact_cadence", None) else self.cadence
+        if m >= fe:
+            return max(fe, 1)
+        # end on a compaction boundary (every m-th timestep of the global step count)
+        return (m - sim.step_index % m) + m * (max(1, round(fe / m)) - 1)
+
     def _enqueue_feedback(self, st, g, last_row):
         """Async copy of a chunk's last tally row and of the device slot counters to pinned memory."""
         import torch
 
+        if not self._fb_pool and not self._fb:  # first use: page-locking is slow, do it once (in the warm-up)
+            self._fb_pool = [torch.empty(18, dtype=torch.int64).pin_memory() for _ in range(4)]
         buf = self._fb_pool.pop() if self._fb_pool else torch.empty(18, dtype=torch.int64).pin_memory()
         buf[:16].copy_(st.tally[last_row - st._row_base], non_blocking=True)
         buf[16:].copy_(g.n_dev, non_blocking=True)
@@ -94,7 +114,7 @@ class FusedPhotonStep(physicl.Step):
                 self.cadence = int(sim.compact_cadence)
             elif live_in > 0:
                 d = died / live_in
-                self.cadence = 64 if d <= 1e-4 else int(min(64, max(1, round(math.sqrt(0.545 / d)))))
+                self.cadence = 64 if d <= 1e-4 else int(min(8, max(1, round(math.sqrt(0.645 / d)))))
             self._fb_pool.append(buf)
 
     # ---- k timesteps with one C-ABI call ----------------------------------------------------------
@@ -142,7 +162,7 @@ class FusedPhotonStep(physicl.Step):
         self._note(sim, first, k, ts)
         last = first + k - 1
         sim._mark_device_dirty(live_row=last)
-        if self.retires and not self.varn and sim.feedback_every and (sim.step_index + k) % sim.feedback_every == 0:
+        if self.retires and not self.varn and sim.feedback_every:
             self._enqueue_feedback(st, g, last)
 
     # ---- one timestep --------------------------------------------------------------------------------

@@ -539,6 +539,49 @@ def test_compacting_step_matches_twin_by_id(ctx, mode, n):
             assert u.same_bits(snap[nm], host[nm]), (step, nm)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [3, 1024, 70_001])
+def test_timesteps_fused_in_registers_equal_single_steps(ctx, mode, n):
+    """pcl_photon_steps advances up to 8 timesteps per launch with the photons held in registers: same
+    tally rows and the same bits as one launch per timestep, and as the binary32 twin stepped on the CPU."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    r, v = u.random_photons(n, seed=40 + n % 7, spread=2e5)
+    E = np.random.default_rng(3).uniform(0.2, 1.0, n) if mode & 1 else None
+    k = 2.0e-7 if mode & 2 else 2.5e-6  # delete mode: ~6 % absorbed per step; else ~75 % scatter
+    planes = [(0, 1.0e5), (2, -5.0e4)]
+    r2 = 1.5e6 ** 2
+    steps = 13  # 8 + 5: a full and a partial group
+    stA, gA = u.make_store(ctx, r, v, E=E, nscat=True)
+    stB, gB = u.make_store(ctx, r, v, E=E, nscat=True)
+    host = u.host_state(gB)
+    sp = _capi.ScatterParams(k=k, c=u.C_LIGHT, mode=mode)
+    pl = _capi.make_planes(planes)
+    first = stA.new_rows(steps)
+    soa = gA.soa()
+    soa.dx = soa.dy = soa.dz = None
+    rg = _capi.Rng(seed=23, step=4)
+    ctx.call("pcl_photon_steps", stA.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(r2),
+             C.byref(pl), stA.row_ptr(first), C.c_uint32(steps))
+    rowsA = np.array([stA.read_row(first + i) for i in range(steps)])
+    rowsB, rowsT = [], []
+    for s in range(steps):
+        rowsB.append(u.photon_step(ctx, stB, gB, 1e-3, k, u.C_LIGHT, mode, seed=23, step=4 + s, r2_escape=r2, planes=planes).copy())
+        rowsT.append(oracle.photon_step_f32(host, 1e-3, k, u.C_LIGHT, mode, seed=23, step=4 + s, r2_escape=np.float32(r2),
+                                            planes=planes))
+    assert np.array_equal(rowsA, np.array(rowsB))
+    assert np.array_equal(rowsA, np.array(rowsT))
+    live = ~np.isnan(gA.download("x"))
+    assert np.array_equal(live, ~np.isnan(host["x"]))
+    if n > 1000:
+        assert live.sum() < n and rowsA[:, _capi.T_ESCAPED].sum() > 0 and rowsA[:, _capi.T_SCATTERED].sum() > 0
+        assert live.sum() > 0 or mode & 2  # delete mode: nobody lasts 13 steps inside this sphere
+    for nm in u.PLANE_NAMES + ("nscat",):
+        assert u.same_bits(gA.download(nm)[live], gB.download(nm)[live]), nm
+        assert u.same_bits(gA.download(nm)[live], host[nm][live]), nm
+
+
 def test_pingpong_loop_equals_in_place_loop(ctx):
     """pcl_photon_steps_pp (compaction every m steps, slot count kept on the device) gives the same
     tallies and the same surviving photons as the plain in-place loop."""
