@@ -125,7 +125,9 @@ int pcl_stream_sync(pcl_ctx *ctx, uintptr_t stream);
  * that integrator is not in the reference (Object.a is never read). */
 int pcl_kinematics(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
                    const float *a_uniform);
-/* nsteps back-to-back kinematics steps replayed from a CUDA graph (one launch per step). */
+/* nsteps timesteps of equal dt in ONE launch: particles do not interact, so each thread keeps its
+ * particles in registers for all nsteps and the state crosses HBM once.  Bit-identical to nsteps
+ * calls of pcl_kinematics; dr holds the last step's displacement (newton.py:15). */
 int pcl_kinematics_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
                          const float *a_uniform, uint32_t nsteps);
 

@@ -8,12 +8,14 @@
 // One thread moves 4 consecutive particles per plane with 128-bit accesses; a warp therefore
 // touches 512 contiguous bytes of each plane.  The grid is persistent (a multiple of the SM
 // count) and walks tiles in grid-stride order.
+#include <stdlib.h>
+
 #include "pcl_common.cuh"
 
 // ACCEL: 0 = reference law, 1 = per-particle a planes, 2 = uniform a
 template <int ACCEL, bool WRITE_DR>
 __global__ void __launch_bounds__(PCL_BLOCK)
-pcl_k_kinematics(pcl_soa p, float dt, float aux, float auy, float auz, uint64_t nvec) {
+pcl_k_kinematics(pcl_soa p, float dt, float aux, float auy, float auz, uint64_t nvec, uint32_t nsteps) {
     const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
     for (uint64_t g = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; g < nvec; g += stride) {
         const uint64_t i = g * 4;
@@ -25,7 +27,10 @@ pcl_k_kinematics(pcl_soa p, float dt, float aux, float auy, float auz, uint64_t 
             ay = pcl_ld4(p.ay + i);
             az = pcl_ld4(p.az + i);
         }
-        float4 dx, dy, dz;
+        float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), dy = dx, dz = dx;
+        // nsteps timesteps in registers: the same binary32 operations in the same order as nsteps
+        // launches, so the result is bit-identical; only the last dr is observable
+        for (uint32_t st = 0; st < nsteps; ++st)
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             if (ACCEL == 1) {
@@ -63,23 +68,37 @@ pcl_k_kinematics(pcl_soa p, float dt, float aux, float auy, float auz, uint64_t 
 // scalar tail (n % 4 particles) and unaligned fallback
 template <int ACCEL, bool WRITE_DR>
 __global__ void pcl_k_kinematics_tail(pcl_soa p, float dt, float aux, float auy, float auz,
-                                      uint64_t begin, uint64_t end) {
+                                      uint64_t begin, uint64_t end, uint32_t nsteps) {
     uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= end) return;
+    float x = p.x[i], y = p.y[i], z = p.z[i];
     float vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
+    float ax = 0.f, ay = 0.f, az = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
     if (ACCEL == 1) {
-        vx = vx + p.ax[i] * dt;
-        vy = vy + p.ay[i] * dt;
-        vz = vz + p.az[i] * dt;
-    } else if (ACCEL == 2) {
-        vx = vx + aux * dt;
-        vy = vy + auy * dt;
-        vz = vz + auz * dt;
+        ax = p.ax[i];
+        ay = p.ay[i];
+        az = p.az[i];
     }
-    float dx = vx * dt, dy = vy * dt, dz = vz * dt;
-    p.x[i] = p.x[i] + dx;
-    p.y[i] = p.y[i] + dy;
-    p.z[i] = p.z[i] + dz;
+    for (uint32_t st = 0; st < nsteps; ++st) {
+        if (ACCEL == 1) {
+            vx = vx + ax * dt;
+            vy = vy + ay * dt;
+            vz = vz + az * dt;
+        } else if (ACCEL == 2) {
+            vx = vx + aux * dt;
+            vy = vy + auy * dt;
+            vz = vz + auz * dt;
+        }
+        dx = vx * dt;
+        dy = vy * dt;
+        dz = vz * dt;
+        x = x + dx;
+        y = y + dy;
+        z = z + dz;
+    }
+    p.x[i] = x;
+    p.y[i] = y;
+    p.z[i] = z;
     if (ACCEL != 0) {
         p.vx[i] = vx;
         p.vy[i] = vy;
@@ -93,7 +112,7 @@ __global__ void pcl_k_kinematics_tail(pcl_soa p, float dt, float aux, float auy,
 }
 
 template <int ACCEL, bool WRITE_DR>
-static int launch_kin(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, float dt, const float *au) {
+static int launch_kin(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, float dt, const float *au, uint32_t nsteps) {
     bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) &&
                    pcl_aligned16(p.vx) && pcl_aligned16(p.vy) && pcl_aligned16(p.vz);
     if (WRITE_DR) aligned = aligned && pcl_aligned16(p.dx) && pcl_aligned16(p.dy) && pcl_aligned16(p.dz);
@@ -101,21 +120,21 @@ static int launch_kin(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, float dt,
     uint64_t nvec = aligned ? p.n / 4 : 0;
     if (nvec) {
         unsigned grid = pcl_stream_grid(ctx, nvec, PCL_BLOCK, 8);
-        pcl_k_kinematics<ACCEL, WRITE_DR><<<grid, PCL_BLOCK, 0, st>>>(p, dt, au[0], au[1], au[2], nvec);
+        pcl_k_kinematics<ACCEL, WRITE_DR><<<grid, PCL_BLOCK, 0, st>>>(p, dt, au[0], au[1], au[2], nvec, nsteps);
         PCL_LAUNCHED(ctx);
     }
     uint64_t begin = nvec * 4;
     if (begin < p.n) {
         uint64_t rem = p.n - begin;
         unsigned grid = (unsigned)((rem + 255) / 256);
-        pcl_k_kinematics_tail<ACCEL, WRITE_DR><<<grid, 256, 0, st>>>(p, dt, au[0], au[1], au[2], begin, p.n);
+        pcl_k_kinematics_tail<ACCEL, WRITE_DR><<<grid, 256, 0, st>>>(p, dt, au[0], au[1], au[2], begin, p.n, nsteps);
         PCL_LAUNCHED(ctx);
     }
     return 0;
 }
 
 static int kin_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, int accel,
-                        const float *a_uniform) {
+                        const float *a_uniform, uint32_t nsteps) {
     PCL_REQUIRE(ctx, p != nullptr, "null particle view");
     PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
@@ -135,65 +154,43 @@ static int kin_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float d
         }
     }
     switch (mode * 2 + (dr ? 1 : 0)) {
-        case 0: return launch_kin<0, false>(ctx, st, *p, dt, au);
-        case 1: return launch_kin<0, true>(ctx, st, *p, dt, au);
-        case 2: return launch_kin<1, false>(ctx, st, *p, dt, au);
-        case 3: return launch_kin<1, true>(ctx, st, *p, dt, au);
-        case 4: return launch_kin<2, false>(ctx, st, *p, dt, au);
-        default: return launch_kin<2, true>(ctx, st, *p, dt, au);
+        case 0: return launch_kin<0, false>(ctx, st, *p, dt, au, nsteps);
+        case 1: return launch_kin<0, true>(ctx, st, *p, dt, au, nsteps);
+        case 2: return launch_kin<1, false>(ctx, st, *p, dt, au, nsteps);
+        case 3: return launch_kin<1, true>(ctx, st, *p, dt, au, nsteps);
+        case 4: return launch_kin<2, false>(ctx, st, *p, dt, au, nsteps);
+        default: return launch_kin<2, true>(ctx, st, *p, dt, au, nsteps);
     }
 }
 
 extern "C" int pcl_kinematics(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
                               const float *a_uniform) {
     PCL_ENTER(ctx);
-    return kin_dispatch(ctx, (cudaStream_t)stream, p, dt, accel, a_uniform);
+    return kin_dispatch(ctx, (cudaStream_t)stream, p, dt, accel, a_uniform, 1);
 }
 
-// nsteps steps as one CUDA graph launch (the graph holds one kernel node per step, so the
-// accounting stays "one HBM round trip per step").  Needed where a step is ~10 us (1M particles):
-// launch gaps would otherwise dominate.
+// nsteps timesteps of equal dt.  Particles do not interact, so a thread keeps its four particles in
+// registers and applies the step nsteps times before writing back: ONE HBM round trip per launch
+// instead of one per timestep, bit-identical to nsteps calls of pcl_kinematics (same binary32
+// operations in the same order; only the last dr is observable, as with the reference's loop,
+// physicl/newton.py:14-16).  PCL_KIN_FUSE caps the timesteps per launch (1 = one launch per timestep,
+// the form the HBM-roofline figures are quoted on).
 extern "C" int pcl_kinematics_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                                     int accel, const float *a_uniform, uint32_t nsteps) {
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, p != nullptr, "null particle view");
     if (nsteps == 0 || p->n == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    pcl_graph_key key;
-    memset(&key, 0, sizeof(key));
-    key.p = *p;
-    key.dt = dt;
-    key.accel = accel;
-    if (a_uniform) memcpy(key.a, a_uniform, sizeof(key.a));
-    key.nsteps = nsteps;
-    key.stream = stream;
-    if (!ctx->kin_graph || memcmp(&key, &ctx->kin_key, sizeof(key)) != 0) {
-        if (ctx->kin_graph) {
-            cudaGraphExecDestroy(ctx->kin_graph);
-            ctx->kin_graph = nullptr;
-        }
-        // capture on a private stream so a legacy default stream argument is acceptable
-        cudaStream_t cap;
-        PCL_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-        PCL_CUDA(ctx, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-        int rc = 0;
-        uint64_t before = ctx->launches;
-        for (uint32_t s = 0; s < nsteps && rc == 0; ++s) rc = kin_dispatch(ctx, cap, p, dt, accel, a_uniform);
-        ctx->launches = before;  // counted at replay time below
-        cudaGraph_t g = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(cap, &g);
-        cudaStreamDestroy(cap);
-        if (rc != 0) {
-            if (g) cudaGraphDestroy(g);
-            return rc;
-        }
-        PCL_CUDA(ctx, ce);
-        PCL_CUDA(ctx, cudaGraphInstantiate(&ctx->kin_graph, g, 0));
-        cudaGraphDestroy(g);
-        ctx->kin_key = key;
+    static int fuse = -1;
+    if (fuse < 0) {
+        const char *e = getenv("PCL_KIN_FUSE");
+        fuse = e ? atoi(e) : 4096;
+        if (fuse < 1) fuse = 1;
     }
-    PCL_CUDA(ctx, cudaGraphLaunch(ctx->kin_graph, st));
-    const uint64_t per_step = (p->n / 4 ? 1 : 0) + (p->n % 4 ? 1 : 0);
-    ctx->launches += (uint64_t)nsteps * per_step;
+    for (uint32_t s = 0; s < nsteps;) {
+        const uint32_t run = nsteps - s < (uint32_t)fuse ? nsteps - s : (uint32_t)fuse;
+        int rc = kin_dispatch(ctx, (cudaStream_t)stream, p, dt, accel, a_uniform, run);
+        if (rc) return rc;
+        s += run;
+    }
     return 0;
 }

@@ -66,7 +66,6 @@ extern "C" int pcl_destroy(pcl_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     pcl_hostpipe_destroy(ctx);
-    if (ctx->kin_graph) cudaGraphExecDestroy(ctx->kin_graph);
     if (ctx->scan_buf) cudaFree(ctx->scan_buf);
     if (ctx->grav_part) cudaFree(ctx->grav_part);
     free(ctx);

@@ -22,15 +22,6 @@
 // most timesteps one photon launch advances in registers (pcl_k_photon_multi)
 #define PCL_FUSE_MAX 8
 
-struct pcl_graph_key {
-    pcl_soa p;
-    float dt;
-    int accel;
-    float a[3];
-    uint32_t nsteps;
-    uintptr_t stream;
-};
-
 struct pcl_hostpipe;  // hostpipe.cu
 
 struct pcl_ctx {
@@ -47,10 +38,6 @@ struct pcl_ctx {
     // gravity: partial accelerations of the j splits
     float *grav_part;
     size_t grav_cap;
-    // cached CUDA graph of a multi-step kinematics loop
-    cudaGraphExec_t kin_graph;
-    pcl_graph_key kin_key;
-    // cached CUDA graph of a multi-step photon loop is rebuilt per call (step index changes)
     pcl_hostpipe *pipe;
 };
 

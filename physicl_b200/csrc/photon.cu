@@ -249,8 +249,11 @@ __device__ __forceinline__ void pcl_tally_to_shared(const uint32_t (&cnt)[NC], u
     }
 }
 
+#ifndef PCL_MULTI_MINB
+#define PCL_MULTI_MINB PCL_PHOTON_MINB
+#endif
 template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
-__global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
+__global__ void __launch_bounds__(PCL_BLOCK, PCL_MULTI_MINB)
 pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     constexpr int NST = COMPACT ? (WAVE ? 9 : 8) : 1;  // staged planes: x y z vx vy vz id nscat [e]

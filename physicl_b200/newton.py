@@ -25,9 +25,22 @@ class NewtonianKinematicsStep(physicl.Step):
         self.a_uniform = None if a_uniform is None else np.asarray(a_uniform, np.float32).reshape(3)
         self.write_dr = write_dr
 
+    def can_run_many(self, sim):
+        return True
+
+    def chunk_steps(self, sim):
+        return 256
+
+    def run_many(self, sim, k, dt, ts):
+        """k timesteps of equal dt with one C-ABI call (``pcl_kinematics_steps``): the particles stay
+        in registers for all k steps, one HBM round trip, same bits as k single steps."""
+        self._launch(sim, float(dt), int(k))
+
     def run(self, sim):
+        self._launch(sim, float(sim.dt), 1)
+
+    def _launch(self, sim, dt, k):
         st = sim.device_store()
-        dt = float(sim.dt)
         au = None
         if self.a_uniform is not None:
             au = self.a_uniform.ctypes.data_as(C.POINTER(C.c_float))
@@ -39,7 +52,11 @@ class NewtonianKinematicsStep(physicl.Step):
             soa = g.soa()
             if self.accel and self.a_uniform is not None:
                 soa.ax = soa.ay = soa.az = None
-            sim.cl_ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(dt), int(self.accel), au)
+            if k == 1:
+                sim.cl_ctx.call("pcl_kinematics", st.stream(), C.byref(soa), C.c_float(dt), int(self.accel), au)
+            else:
+                sim.cl_ctx.call("pcl_kinematics_steps", st.stream(), C.byref(soa), C.c_float(dt), int(self.accel), au,
+                                C.c_uint32(k))
         sim._mark_device_dirty()
 
 

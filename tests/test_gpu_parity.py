@@ -69,23 +69,31 @@ def test_kinematics_unaligned_view_takes_scalar_path(ctx):
         assert u.same_bits(g.download(nm)[1:], host[nm]), nm
 
 
-def test_kinematics_graph_steps_equal_single_steps(ctx):
+@pytest.mark.parametrize("accel", [0, 1, 2])
+def test_kinematics_timesteps_in_registers_equal_single_steps(ctx, accel):
+    """pcl_kinematics_steps (k timesteps per HBM round trip) == k launches of pcl_kinematics == the twin."""
     u = _u()
     n = 200_003
     rng = np.random.default_rng(5)
     r, v = rng.uniform(-1e3, 1e3, (3, n)), rng.normal(0, 10, (3, n))
-    st1, g1 = u.make_store(ctx, r, v, kind="object")
-    st2, g2 = u.make_store(ctx, r, v, kind="object")
+    a = rng.normal(0, 3, (3, n)) if accel == 1 else None
+    st1, g1 = u.make_store(ctx, r, v, a=a, kind="object")
+    st2, g2 = u.make_store(ctx, r, v, a=a, kind="object")
+    for g in (g1, g2):
+        g.ensure("dx", "dy", "dz")
+    host = u.host_state(g2)
     au = np.array([0.0, 0.0, -9.81], np.float32)
-    pau = au.ctypes.data_as(C.POINTER(C.c_float))
-    for _ in range(2):  # second call replays the cached graph
+    pau = au.ctypes.data_as(C.POINTER(C.c_float)) if accel == 2 else None
+    for k in (25, 1, 24):
         s1 = g1.soa()
-        ctx.call("pcl_kinematics_steps", st1.stream(), C.byref(s1), C.c_float(1e-3), 1, pau, C.c_uint32(25))
+        ctx.call("pcl_kinematics_steps", st1.stream(), C.byref(s1), C.c_float(1e-3), accel, pau, C.c_uint32(k))
     for _ in range(50):
         s2 = g2.soa()
-        ctx.call("pcl_kinematics", st2.stream(), C.byref(s2), C.c_float(1e-3), 1, pau)
-    for nm in ("x", "y", "z", "vx", "vy", "vz"):
+        ctx.call("pcl_kinematics", st2.stream(), C.byref(s2), C.c_float(1e-3), accel, pau)
+        oracle.kinematics_f32(host, 1e-3, accel, au if accel == 2 else None)
+    for nm in ("x", "y", "z", "vx", "vy", "vz", "dx", "dy", "dz"):
         assert u.same_bits(g1.download(nm), g2.download(nm)), nm
+        assert u.same_bits(g1.download(nm), host[nm]), nm
 
 
 def test_kinematics_matches_reference_golden(ctx, golden):

@@ -441,3 +441,32 @@ def test_trace_path_marks_retired_photons_and_keeps_their_counts():
             assert np.linalg.norm(row[2 + k - 1]) < 6.0e5 + 3.0e5
     freq = np.array([row[1] for row in rows])
     assert freq.sum() > 0 and freq.max() <= steps
+
+
+def test_bulk_kinematics_equals_stepwise():
+    """Simulation.run_steps on [UpdateTimeStep, NewtonianKinematicsStep]: the bulk form keeps the
+    particles in registers for a whole chunk of timesteps; same bits and same clock as step by step."""
+    n = 100_003
+    rng = np.random.default_rng(9)
+    r = rng.uniform(-1e3, 1e3, (3, n)).astype(np.float32)
+    v = rng.normal(0, 10, (3, n)).astype(np.float32)
+
+    def make():
+        s = phys.Simulation(cl_on=True, exit=lambda x: False)
+        s.add_particles(r, v, kind="object")
+        s.add_step(0, phys.UpdateTimeStep(lambda x: np.double(1e-3)))
+        s.add_step(1, phys.newton.NewtonianKinematicsStep(accel=True, a_uniform=[0, 0, -9.81]))
+        return s
+
+    a, b = make(), make()
+    a.run_steps(300)
+    for _ in range(300):
+        b.run_steps(1)
+    assert len(a.ts) == len(b.ts) == 300 and float(a.t) == float(b.t)
+    ga, gb = a.store.group("object"), b.store.group("object")
+    for nm in ("x", "y", "z", "vx", "vy", "vz", "dx", "dy", "dz"):
+        assert np.array_equal(ga.download(nm).view(np.uint32), gb.download(nm).view(np.uint32)), nm
+    # free fall: z = z0 + vz0 t - g t (t + dt) / 2 for this semi-implicit Euler scheme
+    t, dt = 0.3, 1e-3
+    want = r[2].astype(np.float64) + v[2].astype(np.float64) * t - 9.81 * t * (t + dt) / 2
+    assert np.abs(ga.download("z") - want).max() < 5e-3
