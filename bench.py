@@ -280,6 +280,7 @@ def bench_photon_sphere(args, rank, world, local):
         row = np.zeros(_capi.TALLY_COLS, np.int64)
         n_out = C.c_uint64(0)
         k_e2e = max(3, min(args.steps, 20))
+        host_chunk = int(os.environ.get("PCL_HOST_CHUNK", 1 << 20))  # photons per pipelined chunk (tuning aid)
         state = {"n": n, "up": 0, "down": 0}
 
         def host_step(s):
@@ -287,7 +288,7 @@ def bench_photon_sphere(args, rank, world, local):
             soa.n = state["n"]
             rg = _capi.Rng(seed=SEED, step=s)
             ctx.call("pcl_photon_step_host_compact", C.byref(soa), C.c_float(DT), C.byref(sp), C.byref(rg),
-                     C.c_float(R_ESCAPE ** 2), C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(1 << 20), C.byref(n_out))
+                     C.c_float(R_ESCAPE ** 2), C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(host_chunk), C.byref(n_out))
             state["up"] += 28 * state["n"]
             state["down"] += 28 * n_out.value + 8 * _capi.TALLY_COLS
             state["n"] = n_out.value
@@ -318,16 +319,21 @@ def bench_photon_sphere(args, rank, world, local):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "photon_sphere_16m", "photons_per_gpu": n, "A": 1e-3, "n": 1e-3, "dt": DT,
                    "escape_radius": R_ESCAPE, "seed": SEED, "rng": "philox4x32-10 in-kernel",
-                   "pipeline": "kinematics+scatter+escape+sign tally fused, 1 launch/step, retire-and-compact every m-th step (adaptive m)",
+                   "pipeline": "kinematics+scatter+escape+sign tally fused; a launch advances m timesteps with the photons "
+                               "in registers and writes the survivors densely (adaptive m <= 8)",
+                   "timesteps_per_launch": args.steps / max(int(launches), 1),
                    "l2": "state 384 MiB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)",
                    "live_fraction_mean": live / (n * max(len(fused), 1)), "scattered_fraction": scat / max(live, 1),
                    "escaped_in_window": int(hist[-args.steps:].sum()) if len(hist) else 0},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 737.7e6, "traffic_note": "dram__bytes_read+write of one pcl_k_photon_step_tma launch over 16 Mi live "
-                     "photons (profiles/r1_ncu_full_photon_tma.csv): 44.0 B/photon vs 39.6 B algorithmic",
-                     "peak_source": peak_src, "kernel": "pcl_k_photon_step_tma<0,0,0> (+ pcl_k_photon_step_compact every m-th step)",
-                     "algorithmic_bytes": "(36 + 12 f) B per live photon-step, f = scattered fraction (SURVEY.md 8d)",
+                     "traffic": 881.8e6, "traffic_note": "dram__bytes_read+write of one pcl_k_photon_multi launch advancing 16 Mi "
+                     "photons by 4 timesteps (profiles/r1_ncu_full_photon_multi.csv): 13.1 B per photon-step against 39.6 B "
+                     "algorithmic, because the timesteps are fused in registers; the kernel is issue-bound (70 % of peak issue rate), "
+                     "not DRAM-bound",
+                     "peak_source": peak_src, "kernel": "pcl_k_photon_multi<0,0,0,0,1>",
+                     "algorithmic_bytes": "(36 + 12 f) B per live photon-step, f = scattered fraction (SURVEY.md 8d), summed over the "
+                                          "timesteps of the timed region and divided by its CUDA-event time",
                      "per_rank": True},
         "clocks": clocks.summary(),
     }
@@ -503,7 +509,7 @@ def bench_wavelength(args, rank, world, local):
                    "scattered_fraction": scat / max(live, 1), "l2": "state 1.75 GiB per GPU > L2"},
         "e2e": None, "gpu_launches": int(ctx.launches - l0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": "pcl_k_photon_step_tma<1,0,0>",
+                     "peak_source": peak_src, "kernel": "pcl_k_photon_multi<1,0,0,0,0> (8 timesteps per launch, in place)",
                      "algorithmic_bytes": "(36 + 12 f + 4) B per photon-step (SURVEY.md 8d, w = 1)", "per_rank": True},
         "clocks": clocks.summary(),
     }

@@ -5,11 +5,13 @@
 // :659-662), restated for PCIe Gen5 + B200: the shard is cut into chunks, and chunk c's H2D copies,
 // its kernel and its D2H copies are queued on stream c % PIPE_SLOTS, so the two copy engines and
 // the SMs all stay busy.  Bytes over PCIe per photon-step: 24 B up (r, v) + 24 B down (+4 B e up).
+#include <stdlib.h>
+
 #include "pcl_common.cuh"
 
 int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps);
+                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps, bool keep_count);
 
 #define PIPE_SLOTS 4
 #define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
@@ -23,6 +25,9 @@ struct pcl_hostpipe {
     uint64_t *cnt_pinned;       // [PIPE_SLOTS]
     int64_t *tally_dev;
     int64_t *tally_pinned;
+    cudaEvent_t up_done[PIPE_SLOTS];  // zero-copy form: uploads complete in chunk order
+    cudaEvent_t ready;
+    uint64_t *total_dev;              // survivors of the whole step (all chunks append to one output)
 };
 
 void pcl_hostpipe_destroy(pcl_ctx *ctx) {
@@ -35,6 +40,10 @@ void pcl_hostpipe_destroy(pcl_ctx *ctx) {
         for (int q = 0; q < 9; ++q)
             if (hp->out[s][q]) cudaFree(hp->out[s][q]);
     }
+    for (int s = 0; s < PIPE_SLOTS; ++s)
+        if (hp->up_done[s]) cudaEventDestroy(hp->up_done[s]);
+    if (hp->ready) cudaEventDestroy(hp->ready);
+    if (hp->total_dev) cudaFree(hp->total_dev);
     if (hp->cnt_dev) cudaFree(hp->cnt_dev);
     if (hp->cnt_pinned) cudaFreeHost(hp->cnt_pinned);
     if (hp->tally_dev) cudaFree(hp->tally_dev);
@@ -117,7 +126,7 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
                 r.u_phi = b[10];
             }
         }
-        rc = pcl_photon_step_impl(ctx, st, &d, nullptr, dt, sp, &r, escape_r2, planes, hp->tally_dev, nullptr, 1);
+        rc = pcl_photon_step_impl(ctx, st, &d, nullptr, dt, sp, &r, escape_r2, planes, hp->tally_dev, nullptr, 1, false);
         if (rc) return rc;
         float *dst[6] = {host->x, host->y, host->z, host->vx, host->vy, host->vz};
         for (int q = 0; q < 6; ++q)
@@ -139,10 +148,9 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
 // so the output offset is a running sum of survivor counts; an output region never overtakes a chunk
 // that has not been uploaded yet because a chunk yields at most as many photons as it received.
 // ---------------------------------------------------------------------------------------------
-extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
-                                            const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                                            int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host) {
-    PCL_ENTER(ctx);
+static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                               const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                               int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host) {
     PCL_REQUIRE(ctx, host && sp && rng && tally_row_host && n_out_host, "null argument");
     PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz && host->id,
                 "r, v and id planes are required (ids travel with the photons)");
@@ -156,7 +164,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
     if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
     if (!hp->cnt_dev) {
         PCL_CUDA(ctx, cudaMalloc(&hp->cnt_dev, PIPE_SLOTS * sizeof(uint64_t)));
-        PCL_CUDA(ctx, cudaMallocHost(&hp->cnt_pinned, PIPE_SLOTS * sizeof(uint64_t)));
+        if (!hp->cnt_pinned) PCL_CUDA(ctx, cudaMallocHost(&hp->cnt_pinned, PIPE_SLOTS * sizeof(uint64_t)));
         for (int s = 0; s < PIPE_SLOTS; ++s)
             for (int q = 0; q < 9; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->out[s][q], chunk * sizeof(float)));
     }
@@ -196,7 +204,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
         if (wave) { src.e = in[6]; dst.e = ou[6]; }
         src.id = (uint32_t *)in[7]; dst.id = (uint32_t *)ou[7];
         if (host->nscat) { src.nscat = (uint32_t *)in[8]; dst.nscat = (uint32_t *)ou[8]; }
-        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, 1);
+        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, 1, false);
         if (rc) return rc;
         PCL_CUDA(ctx, cudaMemcpyAsync(hp->cnt_pinned + s, hp->cnt_dev + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (c + 1 >= PIPE_SLOTS) {  // oldest chunk in flight: its slot is needed next
@@ -212,5 +220,106 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
     PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
     *n_out_host = out_off;
+    return 0;
+}
+
+// Is this host plane page-locked and mapped into the device's address space (torch pin_memory(),
+// cudaHostAlloc, pcl_host_register)?  Then kernels can store to it directly; *dev gets the alias.
+static bool host_plane_mapped(const void *h, void **dev) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
+// Zero-copy form of the compacting host-buffer step (PCL_HOST_ZEROCOPY=1 and every plane page-locked and mapped):
+// uploads go through the copy engine chunk by chunk, and each chunk's kernel stores its survivors
+// STRAIGHT into the host planes over PCIe (coalesced runs out of the shared-memory stage), appending
+// at one device-side counter shared by all chunks.  No staging buffers on the way back, no survivor
+// counts read by the host, one synchronisation per timestep; the two PCIe directions run concurrently.
+// In-place safety: uploads complete in chunk order (event chain), a kernel starts after its own
+// upload, and at any moment the survivors written so far number at most the slots of the chunks whose
+// kernels have started, so they only overwrite host regions that are already on the device.
+extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                                            const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                                            int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, host && sp && rng && tally_row_host && n_out_host, "null argument");
+    PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz && host->id,
+                "r, v and id planes are required (ids identify photons afterwards)");
+    PCL_REQUIRE(ctx, rng->u_rand == nullptr, "the compacting host step draws from Philox");
+    const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH;
+    if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
+    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, wave ? host->e : nullptr,
+                        (float *)host->id, (float *)host->nscat};
+    float *dplane[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool mapped = true;
+    static int zero_copy = -1;
+    if (zero_copy < 0) {
+        // measured on B200 / PCIe Gen5 (20 steps of the default bench): staged copies 1.40 G photon-steps/s,
+        // zero-copy stores 1.17-1.22 G, so the staged form is the default and this one is opt-in
+        const char *e = getenv("PCL_HOST_ZEROCOPY");
+        zero_copy = e ? atoi(e) : 0;
+    }
+    for (int q = 0; q < 9 && mapped; ++q)
+        if (hplane[q]) mapped = host_plane_mapped(hplane[q], (void **)&dplane[q]);
+    if (!mapped || !zero_copy)
+        return host_compact_staged(ctx, host, dt, sp, rng, escape_r2, planes, tally_row_host, chunk, n_out_host);
+    if (chunk == 0) chunk = 1u << 20;
+    chunk = (chunk + 3) & ~(uint64_t)3;
+    int rc = pipe_prepare(ctx, chunk);
+    if (rc) return rc;
+    pcl_hostpipe *hp = ctx->pipe;
+    if (!hp->total_dev) {
+        PCL_CUDA(ctx, cudaMalloc(&hp->total_dev, sizeof(uint64_t)));
+        PCL_CUDA(ctx, cudaEventCreateWithFlags(&hp->ready, cudaEventDisableTiming));
+        for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaEventCreateWithFlags(&hp->up_done[s], cudaEventDisableTiming));
+    }
+    if (!hp->cnt_pinned) PCL_CUDA(ctx, cudaMallocHost(&hp->cnt_pinned, PIPE_SLOTS * sizeof(uint64_t)));
+    PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
+    PCL_CUDA(ctx, cudaMemsetAsync(hp->total_dev, 0, sizeof(uint64_t), hp->stream[0]));
+    PCL_CUDA(ctx, cudaEventRecord(hp->ready, hp->stream[0]));
+    const uint64_t nchunks = (host->n + chunk - 1) / chunk;
+    pcl_soa dst;
+    memset(&dst, 0, sizeof(dst));
+    dst.n = host->n;
+    dst.id_base = host->id_base;
+    dst.x = dplane[0]; dst.y = dplane[1]; dst.z = dplane[2]; dst.vx = dplane[3]; dst.vy = dplane[4]; dst.vz = dplane[5];
+    dst.e = dplane[6];
+    dst.id = (uint32_t *)dplane[7];
+    dst.nscat = (uint32_t *)dplane[8];
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % PIPE_SLOTS);
+        cudaStream_t st = hp->stream[s];
+        const uint64_t off = c * chunk;
+        const uint64_t m = (host->n - off < chunk) ? host->n - off : chunk;
+        if (c < PIPE_SLOTS) PCL_CUDA(ctx, cudaStreamWaitEvent(st, hp->ready, 0));
+        if (c > 0) PCL_CUDA(ctx, cudaStreamWaitEvent(st, hp->up_done[(c - 1) % PIPE_SLOTS], 0));
+        float **in = hp->buf[s];
+        for (int q = 0; q < 9; ++q)
+            if (hplane[q]) PCL_CUDA(ctx, cudaMemcpyAsync(in[q], hplane[q] + off, m * sizeof(float), cudaMemcpyHostToDevice, st));
+        PCL_CUDA(ctx, cudaEventRecord(hp->up_done[s], st));
+        pcl_soa src;
+        memset(&src, 0, sizeof(src));
+        src.n = m;
+        src.id_base = host->id_base;
+        src.x = in[0]; src.y = in[1]; src.z = in[2]; src.vx = in[3]; src.vy = in[4]; src.vz = in[5];
+        if (wave) src.e = in[6];
+        src.id = (uint32_t *)in[7];
+        if (host->nscat) src.nscat = (uint32_t *)in[8];
+        pcl_soa d = dst;
+        d.n = m;
+        rc = pcl_photon_step_impl(ctx, st, &src, &d, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->total_dev, 1, true);
+        if (rc) return rc;
+    }
+    for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
+    PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    PCL_CUDA(ctx, cudaMemcpy(hp->cnt_pinned, hp->total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
+    *n_out_host = hp->cnt_pinned[0];
     return 0;
 }

@@ -95,7 +95,7 @@ extern "C" int pcl_stream_sync(pcl_ctx *ctx, uintptr_t stream) {
 
 extern "C" int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes) {
     PCL_ENTER(ctx);
-    PCL_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    PCL_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return 0;
 }
 extern "C" int pcl_host_unregister(pcl_ctx *ctx, void *ptr) {

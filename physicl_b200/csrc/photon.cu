@@ -405,9 +405,14 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             ++rk;
         }
         __syncthreads();
-        // coalesced copy-out: consecutive threads write consecutive survivors
+        // coalesced copy-out: consecutive threads write consecutive survivors, and every warp store
+        // covers one 128-byte ALIGNED line of the output (the tile's range starts anywhere, so the first
+        // lanes of the first line idle): full lines in HBM, full-size packets when `d` is host memory
         const unsigned long long base = s_base;
-        for (uint32_t q = threadIdx.x; q < tot; q += PCL_BLOCK) {
+        const uint32_t skew = (uint32_t)(base & 31ull);
+        for (uint32_t qq = threadIdx.x; qq < tot + skew; qq += PCL_BLOCK) {
+            if (qq < skew) continue;
+            const uint32_t q = qq - skew;
             const unsigned long long o = base + q;
             d.x[o] = s_stage[0][q];
             d.y[o] = s_stage[1][q];
@@ -580,14 +585,14 @@ static uint32_t photon_fuse_max() {
 
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
-                            int64_t *row, uint64_t *n_out, uint32_t nsteps) {
+                            int64_t *row, uint64_t *n_out, uint32_t nsteps, bool keep_count) {
     const bool aligned = pcl_aligned16(p.x) && pcl_aligned16(p.y) && pcl_aligned16(p.z) && pcl_aligned16(p.vx) &&
                          pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
                          pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
                          pcl_aligned16(K.u_rand);
     if (dst) {  // retire-and-compact form: one kernel handles every slot, tail included
         PCL_REQUIRE(ctx, aligned, "the compacting step needs 16-byte aligned planes");
-        PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
+        if (!keep_count) PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
         pcl_k_photon_multi<WAVE, DEL, INJ, PL, true><<<grid, PCL_BLOCK, 0, st>>>(p, *dst, K, row, (unsigned long long *)n_out,
                                                                                   nsteps);
@@ -631,23 +636,23 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
 
 template <bool WAVE, bool DEL, bool INJ>
 static int launch_photon(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
-                         int64_t *row, uint64_t *n_out, uint32_t nsteps) {
-    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, dst, K, row, n_out, nsteps)
-                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, dst, K, row, n_out, nsteps);
+                         int64_t *row, uint64_t *n_out, uint32_t nsteps, bool keep_count) {
+    return K.nplanes ? launch_photon_pl<WAVE, DEL, INJ, true>(ctx, st, p, dst, K, row, n_out, nsteps, keep_count)
+                     : launch_photon_pl<WAVE, DEL, INJ, false>(ctx, st, p, dst, K, row, n_out, nsteps, keep_count);
 }
 
 static int photon_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, const StepK &K,
-                           uint32_t mode, int64_t *row, uint64_t *n_out, uint32_t nsteps) {
+                           uint32_t mode, int64_t *row, uint64_t *n_out, uint32_t nsteps, bool keep_count) {
     const bool wave = mode & PCL_SCATTER_WAVELENGTH, del = mode & PCL_SCATTER_DELETE, inj = K.u_rand != nullptr;
     switch ((wave ? 4 : 0) | (del ? 2 : 0) | (inj ? 1 : 0)) {
-        case 0: return launch_photon<false, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 1: return launch_photon<false, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 2: return launch_photon<false, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 3: return launch_photon<false, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 4: return launch_photon<true, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 5: return launch_photon<true, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        case 6: return launch_photon<true, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps);
-        default: return launch_photon<true, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps);
+        case 0: return launch_photon<false, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 1: return launch_photon<false, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 2: return launch_photon<false, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 3: return launch_photon<false, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 4: return launch_photon<true, false, false>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 5: return launch_photon<true, false, true>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        case 6: return launch_photon<true, true, false>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
+        default: return launch_photon<true, true, true>(ctx, st, *p, dst, K, row, n_out, nsteps, keep_count);
     }
 }
 
@@ -661,9 +666,11 @@ static int check_photon_view(pcl_ctx *ctx, const pcl_soa *p, const pcl_scatter_p
 
 // nsteps timesteps in one launch (1 <= nsteps <= PCL_FUSE_MAX; tally_row: nsteps consecutive rows).
 // dst: write the survivors of the last timestep densely into *dst (count in *n_out) instead of in place.
+// keep_count: *n_out is not reset first, so several launches (the chunks of a host-buffer step) append
+// to one output.
 int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const pcl_soa *dst, float dt,
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps) {
+                         int64_t *tally_row, uint64_t *n_out, uint32_t nsteps, bool keep_count) {
     int rc = check_photon_view(ctx, p, sp);
     if (rc) return rc;
     PCL_REQUIRE(ctx, nsteps >= 1 && nsteps <= PCL_FUSE_MAX, "bad number of timesteps per launch");
@@ -677,7 +684,7 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
         if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, dst->e != nullptr, "dst needs the e plane");
         if (p->nscat) PCL_REQUIRE(ctx, dst->nscat != nullptr, "dst needs the nscat plane");
         if (p->n == 0) {
-            PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
+            if (!keep_count) PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
             return 0;
         }
     }
@@ -685,14 +692,14 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
     StepK K;
     rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
     if (rc) return rc;
-    return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out, nsteps);
+    return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out, nsteps, keep_count);
 }
 
 extern "C" int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                                const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                                const pcl_planes *planes, int64_t *tally_row) {
     PCL_ENTER(ctx);
-    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, nullptr, dt, sp, rng, escape_r2, planes, tally_row, nullptr, 1);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, p, nullptr, dt, sp, rng, escape_r2, planes, tally_row, nullptr, 1, false);
 }
 
 extern "C" int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_soa *dst, float dt,
@@ -700,7 +707,7 @@ extern "C" int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl
                                        const pcl_planes *planes, int64_t *tally_row, uint64_t *n_out_dev) {
     PCL_ENTER(ctx);
     PCL_REQUIRE(ctx, dst != nullptr, "dst is required");
-    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, src, dst, dt, sp, rng, escape_r2, planes, tally_row, n_out_dev, 1);
+    return pcl_photon_step_impl(ctx, (cudaStream_t)stream, src, dst, dt, sp, rng, escape_r2, planes, tally_row, n_out_dev, 1, false);
 }
 
 extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float dt,
@@ -737,7 +744,7 @@ extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong 
         if (compacting) {
             pcl_soa dst = pp->buf[pp->cur ^ 1];
             dst.n = src.n;
-            rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, &r, escape_r2, planes, row, pp->n_dev + (pp->cur ^ 1), run);
+            rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, &r, escape_r2, planes, row, pp->n_dev + (pp->cur ^ 1), run, false);
             if (rc == 0) {
                 pp->buf[pp->cur ^ 1].n = src.n;  // upper bound; the exact count is n_dev[cur]
                 pp->buf[pp->cur ^ 1].id_base = src.id_base;
@@ -745,7 +752,7 @@ extern "C" int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong 
                 pp->id_valid |= 1u << pp->cur;
             }
         } else {
-            rc = pcl_photon_step_impl(ctx, st, &src, nullptr, dt, sp, &r, escape_r2, planes, row, nullptr, run);
+            rc = pcl_photon_step_impl(ctx, st, &src, nullptr, dt, sp, &r, escape_r2, planes, row, nullptr, run, false);
         }
         if (rc) return rc;
         s += run;
@@ -768,7 +775,7 @@ extern "C" int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p
         const uint32_t run = nsteps - s < fuse ? nsteps - s : fuse;
         r.step = rng->step + s;
         int rc = pcl_photon_step_impl(ctx, st, p, nullptr, dt, sp, &r, escape_r2, planes,
-                                      tally_table + (size_t)s * PCL_TALLY_COLS, nullptr, run);
+                                      tally_table + (size_t)s * PCL_TALLY_COLS, nullptr, run, false);
         if (rc) return rc;
         s += run;
     }

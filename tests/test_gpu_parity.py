@@ -630,17 +630,19 @@ def test_pingpong_loop_equals_in_place_loop(ctx):
             assert u.same_bits(sa[nm], sb[nm]), (m, nm)
 
 
-def test_compacting_host_step_equals_resident_steps(ctx):
-    """pcl_photon_step_host_compact: photons in pinned host planes, survivors returned densely; same
-    tallies and the same survivors (by id) as the device-resident path."""
+@pytest.mark.parametrize("pinned", [True, False])
+def test_compacting_host_step_equals_resident_steps(ctx, pinned):
+    """pcl_photon_step_host_compact: photons in host planes (pinned or pageable), survivors returned
+    densely; same tallies and the same survivors (by id) as the device-resident path."""
     from physicl_b200 import _capi
 
     u = _u()
     n = 400_003
     r, v = u.beam_photons(n)
     st, g = u.make_store(ctx, r, v, id_base=7_000_000)
-    host = {nm: torch.from_numpy(g.download(nm).copy()).pin_memory() for nm in u.PLANE_NAMES}
-    host["id"] = torch.arange(n, dtype=torch.int32).pin_memory()
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    host = {nm: pin(torch.from_numpy(g.download(nm).copy())) for nm in u.PLANE_NAMES}
+    host["id"] = pin(torch.arange(n, dtype=torch.int32))
     dt, k, c, r2 = 1e-3, 1e-6, u.C_LIGHT, 1.0e6 ** 2
     n_live = n
     for step in range(8):
