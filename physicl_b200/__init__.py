@@ -465,3 +465,6 @@ class Simulation(threading.Thread):
             with self._state_lock:
                 return self.state_fn(self)
         return self.state_fn(self)
+
+
+from .clprogram import CLInput, CLOutput, CLProgram  # noqa: E402,F401  (physicl/__init__.py:543-664)

@@ -258,13 +258,10 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
                         (float *)host->id, (float *)host->nscat};
     float *dplane[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool mapped = true;
-    static int zero_copy = -1;
-    if (zero_copy < 0) {
-        // measured on B200 / PCIe Gen5 (20 steps of the default bench): staged copies 1.40 G photon-steps/s,
-        // zero-copy stores 1.17-1.22 G, so the staged form is the default and this one is opt-in
-        const char *e = getenv("PCL_HOST_ZEROCOPY");
-        zero_copy = e ? atoi(e) : 0;
-    }
+    // measured on B200 / PCIe Gen5 (20 steps of the default bench): staged copies 1.40 G photon-steps/s,
+    // zero-copy stores 1.17-1.22 G, so the staged form is the default and this one is opt-in
+    const char *zc = getenv("PCL_HOST_ZEROCOPY");
+    const bool zero_copy = zc && atoi(zc) != 0;
     for (int q = 0; q < 9 && mapped; ++q)
         if (hplane[q]) mapped = host_plane_mapped(hplane[q], (void **)&dplane[q]);
     if (!mapped || !zero_copy)

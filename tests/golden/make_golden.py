@@ -396,6 +396,58 @@ def gen_varn(name, expr, wave, n_kwarg, A_kwarg, dt, seed, N=512, nsteps=5):
          kernel_src=np.array(step.prog.kernel_code), **out)
 
 
+def gen_clprogram(seed=21, N=300):
+    """A user-written kernel through the reference's CLInput/CLOutput/CLProgram (physicl/__init__.py:543-664):
+    obj inputs, an obj_def input drawn from np.random, an obj_action type filter, an obj_track list, constants,
+    a double and an int output, an early return.  Half of the objects are photons, which the filter skips."""
+    np.random.seed(seed)
+    rng = np.random.RandomState(seed)
+    objs = []
+    c = physicl.light.c
+    for i in range(N):
+        if i % 2:
+            o = physicl.light.PhotonObject(s=np.zeros(3), v=np.array([c, 0, 0], dtype=np.double), E=np.double(1))
+        else:
+            o = physicl.Object()
+            o.r = physicl.Measurement(list(rng.uniform(-1e3, 1e3, 3)), "m**1")
+            o.v = physicl.Measurement(list(rng.normal(0, 10, 3)), "m**1 s**-1")
+        o.gid = i
+        objs.append(o)
+    body = """
+        int gid = get_global_id(0);
+        double speed = sqrt(pow(v0[gid], 2) + pow(v1[gid], 2) + pow(v2[gid], 2));
+        if (r2[gid] < zcut) { flag[gid] = 0; ke[gid] = NAN; return; }
+        ke[gid] = 0.5 * m * speed * speed + g * r2[gid] + jitter[gid] * exp(-speed / 10.0);
+        flag[gid] = 1;
+    """
+    sim = physicl.Simulation(bounds=np.array([1000, 1000, 1000]), cl_on=True, exit=lambda s: True)
+    sim.add_objs(objs)
+    prog = physicl.CLProgram(sim, "user_energy", body)
+    skip = physicl.CLInput(name="skip", type="obj_action", code="if type(obj) == physicl.light.PhotonObject:\n \t\t continue")
+    v = [physicl.CLInput(name="v%d" % i, type="obj", obj_attr="v[%d]" % i) for i in range(3)]
+    r2 = physicl.CLInput(name="r2", type="obj", obj_attr="r[2]")
+    jit = physicl.CLInput(name="jitter", type="obj_def", obj_def="np.random.random()")
+    who = physicl.CLInput(name="who", type="obj_track", obj_track="obj")
+    consts = [physicl.CLInput(name="m", type="const", const_value="2.5"), physicl.CLInput(name="g", type="const", const_value=str(9.81)),
+              physicl.CLInput(name="zcut", type="const", const_value="-250.0")]
+    prog.prep_metadata = [skip] + v + [r2, jit, who] + consts
+    prog.output_metadata = [physicl.CLOutput(name="ke"), physicl.CLOutput(name="flag", ctype="int")]
+    pyopencl.LAUNCH_LOG.clear()
+    pyopencl.RECORD = True
+    with DrawLog() as log:
+        prog.build_kernel()
+        out = prog.run()
+        u = log.take()
+    pyopencl.RECORD = False
+    la = pyopencl.LAUNCH_LOG[-1]
+    assert len(out["ke"]) == N // 2 and 0 < out["flag"].sum() < N // 2
+    r = np.array([np.asarray(o.r, float) for o in objs]).T.copy()
+    vv = np.array([np.asarray(o.v, float) for o in objs]).T.copy()
+    save("clprogram", N=N, seed=seed, r=r, v=vv, is_photon=np.array([i % 2 for i in range(N)], np.int32), body=np.array(body),
+         jitter=u, ke=out["ke"], flag=np.asarray(out["flag"], np.int32), tracked_gid=np.array([o.gid for o in prog.who], np.int64),
+         m=2.5, g=9.81, zcut=-250.0, c=float(c), **{"in_" + k: a for k, a in la["before"].items()})
+
+
 if __name__ == "__main__":
     gen_iso()
     gen_wave()
@@ -411,3 +463,4 @@ if __name__ == "__main__":
                                                             1000.0, 8000.0),
              True, np.double(5.1e-31 * (532e-9) ** 4), np.double(123.0), 1e-5, seed=19)
     gen_varn("varn_z", "{} * exp(r2[gid] / {})".format(1.0e-3, 2.0e6), False, np.double(1.0e-3), np.double(7.0), 1e-3, seed=20)
+    gen_clprogram()

@@ -261,3 +261,68 @@ def test_simulation_variable_n_fused_equals_unfused():
         assert np.array_equal(ga.download(nm).view(np.uint32), gb.download(nm).view(np.uint32)), nm
     vx0 = float(ra[0][2]) / ra[0][1]
     assert 0.3 < vx0 < 0.7 and len({tuple(x[2:]) for x in ra}) > 1  # something happens from step to step
+
+
+# ---- user kernels through CLProgram ----------------------------------------------------------------
+def test_user_program_matches_the_reference_run(golden):
+    """The reference's own CLProgram ran this user kernel (tests/golden/make_golden.py:gen_clprogram);
+    here the same declarations compile for sm_100a and give the same arrays: the int flags exactly, the
+    float64 energies to 1e-14 (device exp/sqrt/pow against the host libm the reference kernel used)."""
+    import physicl_b200 as physicl
+    from test_jit_host import build_user_program, user_objects
+
+    gd = golden("clprogram")
+    sim = physicl.Simulation(cl_on=True, exit=lambda s: True)
+    sim.add_objs(user_objects(gd))
+    prog = build_user_program(sim, gd)
+    prog.build_kernel()
+    np.random.seed(int(gd["seed"]))
+    out = prog.run()
+    assert out["flag"].dtype == np.int32 and np.array_equal(out["flag"], gd["flag"])
+    cut = gd["flag"] == 0
+    assert np.all(np.isnan(out["ke"][cut]))
+    assert np.allclose(out["ke"][~cut], gd["ke"][~cut], rtol=1e-14, atol=0)
+    assert [o.gid for o in prog.who] == list(gd["tracked_gid"])
+    out2 = prog.run()  # second run: new jitter draws, same structure, module reused
+    assert np.array_equal(out2["flag"], gd["flag"]) and not np.array_equal(out2["ke"][~cut], out["ke"][~cut])
+
+
+def test_user_program_inside_a_step_next_to_device_steps():
+    """A user Step that runs its own kernel on the objects each timestep (the reference's extension
+    story, README.md:8), mixed with the device kinematics step: the objects it sees are the ones the
+    device moved."""
+    import physicl_b200 as physicl
+    import physicl_b200.newton
+
+    class Height(physicl.Step):
+        def __init__(self):
+            self.rows, self.prog = [], None
+
+        def run(self, sim):
+            if self.prog is None:
+                self.prog = physicl.CLProgram(sim, "height", "int gid = get_global_id(0); h[gid] = z[gid] - floor_z; up[gid] = vz[gid] > 0 ? 1 : 0;")
+                self.prog.prep_metadata = [physicl.CLInput(name="z", type="obj", obj_attr="r[2]"), physicl.CLInput(name="vz", type="obj", obj_attr="v[2]"),
+                                           physicl.CLInput(name="floor_z", type="const", const_value="-5.0")]
+                self.prog.output_metadata = [physicl.CLOutput(name="h"), physicl.CLOutput(name="up", ctype="int")]
+                self.prog.build_kernel()
+            self.rows.append(self.prog.run())
+
+    sim = physicl.Simulation(cl_on=True, exit=lambda s: s.t >= 0.0029)
+    rng = np.random.default_rng(1)
+    z0, vz0 = rng.uniform(0, 10, 64), rng.normal(0, 5, 64)
+    for i in range(64):
+        o = physicl.Object()
+        o.r = physicl.Measurement([0.0, 0.0, float(z0[i])], "m**1")
+        o.v = physicl.Measurement([1.0, 0.0, float(vz0[i])], "m**1 s**-1")
+        sim.add_obj(o)
+    h = Height()
+    sim.add_step(0, physicl.UpdateTimeStep(lambda s: np.double(0.001)))
+    sim.add_step(1, physicl.newton.NewtonianKinematicsStep())
+    sim.add_step(2, h)
+    sim.start()
+    sim.join()
+    assert len(h.rows) == 3
+    for k, row in enumerate(h.rows):
+        want = np.float32(z0) + (k + 1) * np.float32(vz0) * np.float32(0.001) + 5.0
+        assert np.allclose(row["h"], want, rtol=0, atol=1e-5)
+        assert np.array_equal(row["up"], (np.float32(vz0) > 0).astype(np.int32))

@@ -630,8 +630,8 @@ def test_pingpong_loop_equals_in_place_loop(ctx):
             assert u.same_bits(sa[nm], sb[nm]), (m, nm)
 
 
-@pytest.mark.parametrize("pinned", [True, False])
-def test_compacting_host_step_equals_resident_steps(ctx, pinned):
+@pytest.mark.parametrize("pinned", [True, False, "zero-copy"])
+def test_compacting_host_step_equals_resident_steps(ctx, pinned, monkeypatch):
     """pcl_photon_step_host_compact: photons in host planes (pinned or pageable), survivors returned
     densely; same tallies and the same survivors (by id) as the device-resident path."""
     from physicl_b200 import _capi
@@ -640,6 +640,8 @@ def test_compacting_host_step_equals_resident_steps(ctx, pinned):
     n = 400_003
     r, v = u.beam_photons(n)
     st, g = u.make_store(ctx, r, v, id_base=7_000_000)
+    # "zero-copy": kernels store the survivors straight into the pinned host planes (opt-in form)
+    monkeypatch.setenv("PCL_HOST_ZEROCOPY", "1" if pinned == "zero-copy" else "0")
     pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
     host = {nm: pin(torch.from_numpy(g.download(nm).copy())) for nm in u.PLANE_NAMES}
     host["id"] = pin(torch.arange(n, dtype=torch.int32))
