@@ -1,0 +1,165 @@
+"""BASELINE.json's configurations at FULL size, checked through properties that do not need a CPU
+replay (the oracle takes minutes at these sizes): conservation of photons row by row, independence
+of the result from how timesteps are grouped into launches and from the compaction cadence,
+uniqueness of the surviving ids, binomial/normal bounds on the stochastic counts, closed-form
+kinematics, Newton's third law."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+import physicl_b200 as phys  # noqa: E402
+import physicl_b200.light  # noqa: E402
+import physicl_b200.newton  # noqa: E402
+from physicl_b200 import _capi  # noqa: E402
+
+C_LIGHT = 299792458.0
+
+
+def _rows(sim, first):
+    st = sim.store
+    rows = np.array([st.read_row(q) for q in range(first, st.current_row + 1)])
+    return rows[rows[:, _capi.T_LIVE_IN] > 0]
+
+
+def _sphere(n, steps, cadence=None, feedback=None):
+    sim = phys.Simulation(cl_on=True, seed=2024, exit=lambda s: False)
+    if cadence:
+        sim.compact_cadence = cadence
+    if feedback:
+        sim.feedback_every = feedback
+    dev = torch.device("cuda", sim.cl_ctx.device)
+    r = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v[0].fill_(C_LIGHT)
+    sim.add_particles(r, v)
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+    esc = phys.light.EscapeSphereStep(3.0e6)
+    sim.add_step(3, esc)
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    sim.add_step(4, sign)
+    sim.run_steps(steps)
+    return sim, esc, sign
+
+
+def test_config1_sphere_16m_conservation_and_policy_independence():
+    n, steps = 16 * 2 ** 20, 45
+    a, esc_a, sign_a = _sphere(n, steps)  # adaptive cadence, up to 8 timesteps per launch
+    rows = _rows(a, 0)
+    assert len(rows) == steps and rows[0, _capi.T_LIVE_IN] == n
+    # every photon is accounted for in every row, and rows chain
+    assert np.array_equal(rows[:, _capi.T_ALIVE], rows[:, _capi.T_LIVE_IN] - rows[:, _capi.T_ESCAPED] - rows[:, _capi.T_ABSORBED])
+    assert np.array_equal(rows[1:, _capi.T_LIVE_IN], rows[:-1, _capi.T_ALIVE])
+    assert rows[:, _capi.T_ABSORBED].sum() == 0 and esc_a.escaped.sum() + rows[-1, _capi.T_ALIVE] == n
+    # R = 3e6 m is a little more than 10 c dt: an unscattered photon leaves in its 11th timestep
+    assert np.all(rows[:10, _capi.T_ESCAPED] == 0) and rows[10, _capi.T_ESCAPED] > 0
+    # scattered ~ Binomial(live, 0.299792458): 5 sigma, every row
+    p = 1e-6 * C_LIGHT * 1e-3
+    live = rows[:, _capi.T_LIVE_IN].astype(np.float64)
+    assert np.all(np.abs(rows[:, _capi.T_SCATTERED] - live * p) <= 5 * np.sqrt(live * p * (1 - p)) + 1)
+    # same photons, one launch per timestep and compaction at every step
+    b, esc_b, sign_b = _sphere(n, steps, cadence=1, feedback=4)
+    assert np.array_equal(_rows(b, 0), rows)
+    assert np.array_equal(np.array(sign_a.data)[:, 1:], np.array(sign_b.data)[:, 1:])
+    # survivors: every id once, identical sets, identical state by id (checked on a checksum of bits)
+    sa, sb = a.store.snapshot("photon"), b.store.snapshot("photon")
+    assert len(sa["id"]) == rows[-1, _capi.T_ALIVE] and np.all(np.diff(sa["id"].astype(np.int64)) > 0)
+    assert np.array_equal(sa["id"], sb["id"])
+    for nm in ("x", "y", "z", "vx", "vy", "vz"):
+        assert int(sa[nm].view(np.uint32).astype(np.uint64).sum()) == int(sb[nm].view(np.uint32).astype(np.uint64).sum()), nm
+    # nobody inside the sphere is missing, nobody outside survived
+    rr = sa["x"].astype(np.float64) ** 2 + sa["y"].astype(np.float64) ** 2 + sa["z"].astype(np.float64) ** 2
+    assert rr.max() < 3.0e6 ** 2 * (1 + 1e-6)
+    # late rows have forgotten the +x start: sign balance at 5 sigma
+    late = np.array(sign_a.data)[-1]
+    assert abs(late[3] - 0.5 * late[1]) <= 5 * np.sqrt(0.25 * late[1])
+
+
+def test_config2_wavelength_64m_scatter_rate_follows_the_energies():
+    n, steps = 64 * 2 ** 20, 6
+    sim = phys.Simulation(cl_on=True, seed=2025, exit=lambda s: False)
+    ctx = sim.cl_ctx
+    dev = torch.device("cuda", ctx.device)
+    E_min = float(phys.light.E_from_wavelength(2500e-9))
+    E_max = float(phys.light.E_from_wavelength(200e-9))
+    e, E0, bins = phys.light.planck_sample_device(ctx, n, E_min, E_max, 5778.0, bins=50000, seed=2025, device=dev, want_bins=True)
+    none = int((bins < 0).sum().item())
+    assert 0 <= none < 1e-3 * n  # the reference's None draws: the mass of the first interval
+    e = torch.nan_to_num(e.contiguous(), nan=0.5)
+    r = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v[0].fill_(C_LIGHT)
+    sim.add_particles(r, v, E=e)
+    A, nd, dt = 5.1e-31 * (532e-9) ** 4, 2.5e25, 1e-5
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True))
+    sim.add_step(3, phys.light.ScatterSignMeasureStep(None, True))
+    sim.device_store().group("photon").e0 = E0
+    sim.run_steps(steps)
+    rows = _rows(sim, 0)
+    assert len(rows) == steps and np.all(rows[:, _capi.T_ALIVE] == n) and np.all(rows[:, _capi.T_LIVE_IN] == n)
+    hc = float(phys.light.h) * float(phys.light.c)
+    pc = (A * nd * C_LIGHT * dt * (E0 / hc) ** 4) * e.double() ** 4  # light.py:300-306 with |dr| = c dt
+    pc = torch.clamp(pc, max=1.0)
+    mean, var = float(pc.sum().item()), float((pc * (1 - pc)).sum().item())
+    assert 0.03 * n < mean < 0.2 * n
+    # |dr| = |v| dt differs from c dt by float32 rounding of the redrawn direction: 1e-6 relative slack
+    assert np.all(np.abs(rows[:, _capi.T_SCATTERED] - mean) <= 5 * np.sqrt(var) + 2e-6 * mean)
+
+
+def test_config0_kinematics_1m_x_1000_closed_form():
+    n, steps, dt = 1_000_000, 1000, 1e-3
+    rng = np.random.default_rng(1234)
+    r0 = rng.uniform(-1e3, 1e3, (3, n)).astype(np.float32)
+    v0 = rng.normal(0, 10, (3, n)).astype(np.float32)
+    sim = phys.Simulation(cl_on=True, exit=lambda s: False)
+    sim.add_particles(r0, v0, kind="object")
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep(accel=True, a_uniform=[0, 0, -9.81]))
+    l0 = sim.cl_ctx.launches
+    sim.run_steps(steps)
+    assert sim.cl_ctx.launches - l0 <= 8  # timesteps are fused in registers: a handful of launches, not 1000
+    g = sim.store.group("object")
+    a = np.array([0.0, 0.0, -9.81])[:, None]
+    # semi-implicit Euler: v_k = v0 + k a dt, r_n = r0 + dt sum_{k=1..n} v_k
+    want_v = v0.astype(np.float64) + steps * a * np.float32(dt)
+    want_r = r0.astype(np.float64) + steps * v0.astype(np.float64) * dt + a * dt * dt * steps * (steps + 1) / 2
+    got_r = np.stack([g.download(q) for q in ("x", "y", "z")]).astype(np.float64)
+    got_v = np.stack([g.download(q) for q in ("vx", "vy", "vz")]).astype(np.float64)
+    # binary32 accumulation: at most half an ulp per step, ulp(|v| < 64) = 3.8e-6, ulp(|r| < 2048) = 1.2e-4;
+    # that is 3e-8 relative per step, far inside the north star's 1e-5 per step
+    assert np.abs(got_v - want_v).max() <= steps * 0.5 * 2.0 ** -18
+    assert np.abs(got_r - want_r).max() <= steps * 0.5 * 2.0 ** -13
+    assert np.allclose(g.download("dz"), got_v[2] * np.float32(dt), rtol=1e-6)
+
+
+def test_config3_gravity_256k_third_law_and_scaling():
+    n = 262144
+    rng = np.random.default_rng(7)
+    m_r = rng.uniform(0, 1, n)
+    rad = 1.0 / np.sqrt(np.maximum(m_r ** (-2.0 / 3.0) - 1.0, 1e-12))
+    d = rng.normal(size=(3, n))
+    pos = rad * d / np.linalg.norm(d, axis=0)
+    vel = np.zeros((3, n))
+    sim = phys.Simulation(cl_on=True, exit=lambda s: False)
+    sim.add_particles(pos, vel, kind="object")
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+    sim.add_step(1, phys.newton.NewtonianGravityStep(G=1.0, eps2=1e-4, masses=np.full(n, 1.0 / n, np.float32)))
+    sim.run_steps(1)
+    g = sim.store.group("object")
+    v = np.stack([g.download(q) for q in ("vx", "vy", "vz")]).astype(np.float64)  # v = a dt after one step from rest
+    acc = v / 1e-3
+    # equal masses: sum of accelerations vanishes (Newton's third law) up to float32 summation error
+    assert np.abs(acc.sum(axis=1)).max() <= 2e-5 * np.abs(acc).sum(axis=1).max()
+    # the cluster pulls inwards: a . r < 0 for (nearly) every body, and |a| matches the enclosed-mass estimate
+    rr = np.linalg.norm(pos, axis=0)
+    inward = (acc * pos).sum(axis=0) < 0
+    assert inward.mean() > 0.995
+    sel = (rr > 0.5) & (rr < 2.0)
+    a_r = -(acc * pos).sum(axis=0) / rr
+    plummer = rr / (rr ** 2 + 1.0) ** 1.5  # G M r / (r^2 + a^2)^(3/2), the smooth Plummer field
+    assert np.median(np.abs(a_r[sel] / plummer[sel] - 1.0)) < 0.05
