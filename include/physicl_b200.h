@@ -150,8 +150,10 @@ int pcl_escape(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float r2, int64
 int pcl_photon_step(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                     const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                     const pcl_planes *planes, int64_t *tally_row);
-/* nsteps fused steps; rng->step is the first step index; tally_table is
- * int64[nsteps][PCL_TALLY_COLS] in device memory, zeroed here. */
+/* nsteps timesteps; rng->step is the first step index; tally_table is int64[nsteps][PCL_TALLY_COLS]
+ * in device memory, zeroed here (one row per timestep).  Photons do not interact, so a launch keeps
+ * its photons in registers for up to 8 timesteps (PCL_PHOTON_FUSE, default 8; 1 = one launch per
+ * timestep) and the state crosses HBM once per launch; results are bit-identical either way. */
 int pcl_photon_steps(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt,
                      const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                      const pcl_planes *planes, int64_t *tally_table, uint32_t nsteps);
@@ -165,8 +167,9 @@ int pcl_photon_step_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, 
                             float dt, const pcl_scatter_params *sp, const pcl_rng *rng,
                             float escape_r2, const pcl_planes *planes, int64_t *tally_row,
                             uint64_t *n_out_dev);
-/* nsteps fused steps over a ping-pong pair: step s runs in place, except that every step with
- * (rng->step + s + 1) % compact_every == 0 is a retire-and-compact step (compact_every = 0: never).
+/* nsteps timesteps over a ping-pong pair: the survivors are written densely into the partner buffer
+ * after every timestep with (rng->step + s + 1) % compact_every == 0 (compact_every = 0: never).  A
+ * launch covers the timesteps up to the next such boundary (at most 8) with the photons in registers.
  * pp->cur and the upper bounds pp->buf[].n are updated; exact counts stay on the device. */
 int pcl_photon_steps_pp(pcl_ctx *ctx, uintptr_t stream, pcl_pingpong *pp, float dt,
                         const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,

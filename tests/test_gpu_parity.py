@@ -671,3 +671,34 @@ def test_compacting_host_step_equals_resident_steps(ctx, pinned, monkeypatch):
     assert np.array_equal(ids[order], snap["id"])
     for nm in u.PLANE_NAMES:
         assert u.same_bits(host[nm].numpy()[:n_live][order], snap[nm]), nm
+
+
+def test_empty_and_tiny_inputs_through_every_bulk_entry_point(ctx):
+    """n = 0 is a no-op everywhere (the reference's loops simply do not execute); rows stay zero."""
+    from physicl_b200 import _capi, jit
+
+    u = _u()
+    for n in (0, 1, 2):
+        r, v = u.beam_photons(n)
+        st, g = u.make_store(ctx, r, v, E=np.ones(n))
+        sp = _capi.ScatterParams(k=1e-6, c=u.C_LIGHT, mode=0)
+        pl = _capi.make_planes([(0, 1.0e5)])
+        rg = _capi.Rng(seed=1, step=0)
+        first = st.new_rows(9)
+        soa = g.soa()
+        soa.dx = soa.dy = soa.dz = None
+        ctx.call("pcl_photon_steps", st.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0),
+                 C.byref(pl), st.row_ptr(first), C.c_uint32(9))
+        rows = np.array([st.read_row(first + i) for i in range(9)])
+        assert np.all(rows[:, _capi.T_LIVE_IN] == n) and np.all(rows[:, _capi.T_ALIVE] == n)
+        ctx.call("pcl_kinematics_steps", st.stream(), C.byref(soa), C.c_float(1e-3), 0, None, C.c_uint32(17))
+        if n:
+            assert np.allclose(g.download("x"), (9 + 17) * np.float32(u.C_LIGHT) * np.float32(1e-3), rtol=1e-6) or rows[:, _capi.T_SCATTERED].sum() > 0
+        mod = jit.Module(ctx, jit.photon_source("1e-6", False))
+        vn = _capi.VarnParams(kd=1.0, e0=1.0, a_slot=1.0, n_slot=1.0)
+        first = st.new_rows(3)
+        ctx.call("pcl_photon_steps_jit", st.stream(), mod.kernel("pcl_jit_photon_step"), C.byref(soa), C.c_float(1e-3), C.byref(sp),
+                 C.byref(vn), C.byref(rg), C.c_float(0.0), C.byref(pl), st.row_ptr(first), C.c_uint32(3))
+        rows = np.array([st.read_row(first + i) for i in range(3)])
+        assert np.all(rows[:, _capi.T_LIVE_IN] == n)
+        mod.close()
