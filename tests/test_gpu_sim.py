@@ -470,3 +470,58 @@ def test_bulk_kinematics_equals_stepwise():
     t, dt = 0.3, 1e-3
     want = r[2].astype(np.float64) + v[2].astype(np.float64) * t - 9.81 * t * (t + dt) / 2
     assert np.abs(ga.download("z") - want).max() < 5e-3
+
+
+def test_presentation_example_2_runs_with_only_the_import_changed():
+    """examples/presentation_example_2.ipynb (cells 0, 1, 3, 4 without the plotting): plane atmosphere
+    n(z) as an OpenCL-C expression, Rayleigh law, Planck energies, TracePathMeasureStep, threaded run
+    polled through get_state().  One photon gets E = None, which planck_phot_distribution may return
+    (light.py:102-104): the reference uploads it as NaN and it never scatters."""
+    import time
+
+    light, newton = phys.light, phys.newton
+    n_0 = phys.Measurement(2.5e25, "m**-3")
+    z_0 = phys.Measurement(8.6e3, "m**1")
+    cl_n2 = "{} * exp(r2[gid] / {})".format(n_0, z_0)
+    np.random.seed(4)
+    T = 5778
+    E = [light.planck_phot_distribution(light.E_from_wavelength(200e-9), light.E_from_wavelength(2500e-9), T, bins=50000)
+         for x in range(300)]
+    E[5] = None
+    phot = light.generate_photons_from_E(E)
+    for p in phot:
+        p.r = phys.Measurement([-150e3, np.random.uniform(-50e3, 50e3), np.random.uniform(0, 100e3)], "m**1")
+    start = np.array([np.asarray(p.r, float) for p in phot])
+    runtime = ((50 * 3 + 50) * 1e3 / light.c) * 0.1  # the notebook runs 5 crossing times (333 steps); 0.1 is enough here
+    A_targ = phys.Measurement(5.1e-31, "m**2") * (phys.Measurement(532e-9, "m**1") ** 4)
+    sim = phys.Simulation(cl_on=True, exit=lambda cond: cond.t >= runtime)
+    sim.add_step(2, phys.UpdateTimeStep(lambda t: phys.Measurement(0.00001, "s**1")))
+    sim.add_step(1, newton.NewtonianKinematicsStep())
+    sim.add_step(3, light.ScatterIsotropicStep(A=A_targ, variable_n=True, variable_n_fn=cl_n2, wavelength_dep_scattering=True))
+    tp = light.TracePathMeasureStep(None)
+    sim.add_step(0, tp)
+    sim.add_objs(phot)
+    sim.start()
+    states = []
+    while sim.running:
+        time.sleep(0.05)
+        states.append(sim.get_state())
+    sim.join()
+    assert states and states[-1]["objects"] == 300
+    nsteps = len(sim.ts)
+    assert nsteps == int(np.ceil(float(runtime) / 1e-5)) and tp.data[0][0] == "t" and len(tp.data) == 301
+    c, dt = float(light.c), 1e-5
+    path = np.array([[np.asarray(q, float) for q in row[1:1 + nsteps]] for row in tp.data[1:]])  # (300, steps, 3)
+    # steps run in INSERTION order (physicl/__init__.py:514), so the tracer (idx 0, added last) runs last: column k
+    # holds the position after k + 1 timesteps
+    assert np.allclose(path[:, 0], start + np.array([c * dt, 0.0, 0.0]), rtol=1e-6)
+    hops = np.linalg.norm(np.diff(path, axis=1), axis=2)
+    assert np.allclose(hops, c * dt, rtol=2e-5)  # every photon moves c dt per step, whatever its direction
+    # the E = None photon never scatters: it keeps flying along +x
+    assert np.allclose(path[5, :, 1:], start[5, 1:], rtol=1e-6) and np.allclose(np.diff(path[5, :, 0]), c * dt, rtol=1e-5)
+    # with variable_n the reference's kernel scalar `A` is the step's n (= 1, light.py:273, :287), so the collision
+    # probability is huge at these densities and every other photon is redirected in every step: after the first
+    # hop nobody is still on the +x axis direction
+    dirs = np.diff(path, axis=1) / (c * dt)
+    others = np.delete(np.arange(300), 5)
+    assert np.all(np.abs(dirs[others, 0, 0] - 1.0) > 1e-6)
