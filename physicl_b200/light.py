@@ -116,10 +116,11 @@ def planck_phot_distribution(E_min, E_max, T, bins=1000):
     return physicl.Measurement(E[x], "J**1")
 
 
-def planck_sample_device(ctx, n, E_min, E_max, T, bins=1000, seed=0, id_base=0, device=None, want_bins=False):
+def planck_sample_device(ctx, n, E_min, E_max, T, bins=1000, seed=0, id_base=0, device=None, want_bins=False, timing=None):
     """Device form of the same sampler for bulk emission: one Philox uniform per photon (stream 1),
     binary search of the float64 table.  Returns ``(e, E0[, bin])``: ``e`` is a float32 CUDA tensor of
-    ``E / E0`` with ``E0 = E_max``; ``bin`` (int32) is the grid index, -1 where the reference yields None."""
+    ``E / E0`` with ``E0 = E_max``; ``bin`` (int32) is the grid index, -1 where the reference yields None.
+    ``timing``: a dict that receives ``device_ms``, the CUDA-event time of the sampling launches."""
     import torch
 
     E, _, cdf = planck_table(E_min, E_max, T, bins)
@@ -130,10 +131,17 @@ def planck_sample_device(ctx, n, E_min, E_max, T, bins=1000, seed=0, id_base=0, 
     b = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_bins else None
     step = (E[-1] - E[0]) / (len(E) - 1)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timing is not None else None
+    if ev:
+        ev[0].record(torch.cuda.current_stream(dev))
     ctx.call("pcl_planck_sample", stream, C.c_uint64(n), C.c_uint64(id_base), C.c_uint64(seed), C.c_void_p(cdf_d.data_ptr()),
              C.c_uint32(cdf.size), C.c_float(E[0] / E0), C.c_float(step / E0), C.c_void_p(e.data_ptr()),
              C.c_void_p(b.data_ptr()) if b is not None else None)
+    if ev:
+        ev[1].record(torch.cuda.current_stream(dev))
     torch.cuda.current_stream(dev).synchronize()  # cdf_d may be freed after return
+    if ev:
+        timing["device_ms"] = ev[0].elapsed_time(ev[1])  # the sampling kernels alone (the table is built on the host)
     return (e[:n], E0, b[:n]) if want_bins else (e[:n], E0)
 
 
