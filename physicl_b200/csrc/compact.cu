@@ -5,9 +5,10 @@
 // Three launches, all HBM-bound:
 //   1. per-tile live counts            reads x                        4 B / slot
 //   2. exclusive scan of tile counts   one block, ntiles * 4 B
-//   3. scatter                         re-reads x, moves every plane  4 B / slot + 2 * B_state / live
-// Ranks inside a tile come from warp ballots + popc, so a warp with no live lane does no stores,
-// and the order of survivors is preserved (results never depend on block scheduling).
+//   3. move                            re-reads x, moves every plane  (4 + B_state) B / slot + B_state / live
+// Ranks inside a tile come from 4-bit live masks + a shuffle scan, survivors are staged in shared
+// memory and written as contiguous runs; the order of survivors is preserved (results never depend on
+// block scheduling).
 #include "pcl_common.cuh"
 
 #define PCL_TILE (PCL_BLOCK * 4)
@@ -68,10 +69,23 @@ __global__ void __launch_bounds__(1024) pcl_k_scan_tiles(uint32_t *counts, uint3
     if (threadIdx.x == 1023) *total_out = s_sum[1023];
 }
 
+// One tile (1024 slots) per CTA.  Every plane is read with 128-bit loads, its survivors are staged in
+// shared memory at their rank inside the tile and then written out as one contiguous, coalesced run
+// (128-byte aligned lines, as in the retire-and-compact photon kernel), plane after plane.
+__device__ __forceinline__ float4 pcl_ld4_guarded(const float *p, uint64_t i, uint64_t n) {
+    if (i + 3 < n) return pcl_ld4(p + i);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < 4; ++l)
+        if (i + l < n) pcl_f4(v, l) = p[i + l];
+    return v;
+}
+
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_compact(pcl_soa s, pcl_soa d, const uint32_t *offsets) {
     __shared__ uint32_t s_w[PCL_WARPS];
+    __shared__ float s_stage[PCL_TILE];
     const uint64_t i = ((uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x) * 4;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t m = (i < s.n) ? pcl_live_mask4(s.x, i, s.n) : 0u;
     const uint32_t c = __popc(m);
     // exclusive rank of this thread's first survivor inside the tile
@@ -79,41 +93,43 @@ pcl_k_compact(pcl_soa s, pcl_soa d, const uint32_t *offsets) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((threadIdx.x & 31) >= o) inc += v;
+        if (lane >= (uint32_t)o) inc += v;
     }
-    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
-    uint32_t wbase = 0;
+    uint32_t wbase = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < PCL_WARPS; ++w)
-        if (w < (int)(threadIdx.x >> 5)) wbase += s_w[w];
-    if (__ballot_sync(0xffffffffu, m != 0u) == 0u) return;  // whole warp retired: nothing to move
-    if (!m) return;
-    uint64_t o = (uint64_t)offsets[blockIdx.x] + wbase + (inc - c);
+    for (int w = 0; w < PCL_WARPS; ++w) {
+        const uint32_t t = s_w[w];
+        wbase += (w < (int)wid) ? t : 0u;
+        tot += t;
+    }
+    if (tot == 0) return;  // whole tile retired: nothing to move
+    const uint32_t rank = wbase + (inc - c);
+    const uint64_t base = offsets[blockIdx.x];
+    const uint32_t skew = (uint32_t)(base & 31ull);
+    const float *src[15] = {s.x, s.y, s.z, s.vx, s.vy, s.vz, s.dx, s.dy, s.dz, s.ax, s.ay, s.az, s.e, (const float *)s.nscat,
+                            (const float *)s.id};
+    float *dst[15] = {d.x, d.y, d.z, d.vx, d.vy, d.vz, d.dx, d.dy, d.dz, d.ax, d.ay, d.az, d.e, (float *)d.nscat, (float *)d.id};
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        if (!(m & (1u << l))) continue;
-        const uint64_t a = i + l;
-        d.x[o] = s.x[a];
-        d.y[o] = s.y[a];
-        d.z[o] = s.z[a];
-        d.vx[o] = s.vx[a];
-        d.vy[o] = s.vy[a];
-        d.vz[o] = s.vz[a];
-        if (s.dx && d.dx) {
-            d.dx[o] = s.dx[a];
-            d.dy[o] = s.dy[a];
-            d.dz[o] = s.dz[a];
+    for (int q = 0; q < 15; ++q) {
+        const bool is_id = q == 14;
+        if (!dst[q] || (!src[q] && !is_id)) continue;  // a plane moves when both sides have it; ids always do
+        float4 v;
+        if (src[q]) {
+            v = (i < s.n) ? pcl_ld4_guarded(src[q], i, s.n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {  // no id plane yet: the id of a slot is its index
+            v = make_float4(__uint_as_float((uint32_t)i), __uint_as_float((uint32_t)i + 1u), __uint_as_float((uint32_t)i + 2u),
+                            __uint_as_float((uint32_t)i + 3u));
         }
-        if (s.ax && d.ax) {
-            d.ax[o] = s.ax[a];
-            d.ay[o] = s.ay[a];
-            d.az[o] = s.az[a];
-        }
-        if (s.e && d.e) d.e[o] = s.e[a];
-        if (s.nscat && d.nscat) d.nscat[o] = s.nscat[a];
-        d.id[o] = s.id ? s.id[a] : (uint32_t)a;
-        ++o;
+        uint32_t rk = rank;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if (m & (1u << l)) s_stage[rk++] = pcl_f4(v, l);
+        __syncthreads();
+        for (uint32_t qq = threadIdx.x; qq < tot + skew; qq += PCL_BLOCK)
+            if (qq >= skew) dst[q][base + (qq - skew)] = s_stage[qq - skew];
+        __syncthreads();
     }
 }
 
