@@ -153,6 +153,8 @@ def sum_over_ranks(x, world):
 # CPU arm: the reference's law in float64, OpenMP over all host cores (oracle port)
 # ---------------------------------------------------------------------------------------------
 def cpu_photon_sphere(n, steps, warmup):
+    if "oracle" not in sys.modules:  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     import oracle
 
     st = {k: np.zeros(n) for k in ("x", "y", "z", "vx", "vy", "vz")}
