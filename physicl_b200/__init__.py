@@ -173,7 +173,10 @@ class Simulation(threading.Thread):
         self.seed = 0
         self.fuse = True
         self.shard = False
-        self.feedback_every = 8  # timesteps per device chunk (one C-ABI call, one asynchronous tally read-back)
+        # timesteps per device chunk (one C-ABI call, one asynchronous tally read-back).  Large on purpose: a chunk is
+        # queued in ~0.1 ms of host time, so the GPU keeps running through host-side hiccups (other ranks' threads,
+        # the scheduler); the retirement policy needs no finer feedback (physicl_b200/fused.py)
+        self.feedback_every = 64
         self.compact_cadence = None  # every m-th timestep retires-and-compacts; None = adaptive
         for attr, val in kwargs.items():
             setattr(self, attr, val)
@@ -365,9 +368,18 @@ class Simulation(threading.Thread):
                 s.prepare(self)
         if not (self.fuse and self.cl_on):
             return steps
+        # the fused plan (and with it the fused step's adaptive cadence and pinned feedback buffers) is kept as
+        # long as the step list stays the same: page-locking buffers inside every run_steps call costs
+        # milliseconds when several ranks do it at once
+        key = tuple(id(s) for s in steps)
+        cached = getattr(self, "_plan_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         from .fused import fuse_plan
 
-        return fuse_plan(steps)
+        plan = fuse_plan(steps)
+        self._plan_cache = (key, plan, steps)  # `steps` keeps the ids alive
+        return plan
 
     def run(self):
         self.start_time = time.time()

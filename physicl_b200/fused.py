@@ -14,20 +14,20 @@ integer/FP32 pipes, not by DRAM.
 
 Retirement policy.  When the pipeline can retire photons (delete scattering, escape sphere) the
 step runs on the store's ping-pong plane sets through ``pcl_photon_steps_pp``: a launch covers m
-timesteps and writes the survivors of the last one densely into the partner buffer.  Photons that
-die inside a launch idle in their lanes until it ends (a fraction ~ d (m-1)/2 of the issue slots for
-a death rate d per step) while the load/compaction phase of a launch costs about a third of a
-timestep's instructions: the cost per live photon-step is ~ 1 + d (m-1)/2 + 0.32/m, minimal at
-m = sqrt(0.645 / d), capped at the 8 timesteps a launch can hold.  d comes from the tally rows with a
-lag: after every chunk (one C-ABI call, about ``sim.feedback_every`` timesteps) the last row and the
-device slot counters are copied to pinned host memory asynchronously, and the host reads them one or
-two chunks later (it only ever waits on work the GPU has long finished), so the stepping loop has no
-blocking host<->device round trip.
+timesteps and writes the survivors of the last one densely into the partner buffer, ALWAYS (a
+compacting launch moves 56 B per slot against 48 B for an in-place one, and neither is the bound).
+Photons that die inside a launch idle in their lanes until it ends (a fraction ~ d (m-1)/2 of the
+issue slots for a death rate d per step) while the load/compaction phase of a launch costs about a
+third of a timestep's instructions: the cost per live photon-step is ~ 1 + d (m-1)/2 + 0.32/m, which is
+flat between m = 4 and m = 8 for the death rates seen here, so m is 8 while (almost) nothing dies and
+4 otherwise.  d comes from the tally rows with a lag: after every chunk (one C-ABI call, about
+``sim.feedback_every`` timesteps) the last row and the device slot counters are copied to pinned host
+memory asynchronously, and the host reads them one or two chunks later (it only ever waits on work the
+GPU has long finished), so the stepping loop has no blocking host<->device round trip.
 """
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import physicl_b200 as physicl
 
@@ -75,7 +75,7 @@ class FusedPhotonStep(physicl.Step):
 
     def chunk_steps(self, sim):
         """Timesteps per C-ABI call: a whole number of compaction periods close to sim.feedback_every."""
-        fe = int(sim.feedback_every) if sim.feedback_every else 8
+        fe = int(sim.feedback_every) if sim.feedback_every else 64
         if not self.retires or self.varn:
             return max(fe, 1)
         m = int(sim.compact_cadence) if getattr(sim, "compact_cadence", None) else self.cadence
@@ -113,8 +113,9 @@ class FusedPhotonStep(physicl.Step):
             if getattr(sim, "compact_cadence", None):
                 self.cadence = int(sim.compact_cadence)
             elif live_in > 0:
-                d = died / live_in
-                self.cadence = 64 if d <= 1e-4 else int(min(8, max(1, round(math.sqrt(0.645 / d)))))
+                # two levels are enough (measured flat between 4 and 8 at d = 6.5 %, section 4 of DESIGN.md), and a
+                # stale estimate then costs a few per cent at worst
+                self.cadence = 8 if died / live_in < 0.02 else 4
             self._fb_pool.append(buf)
 
     # ---- k timesteps with one C-ABI call ----------------------------------------------------------
