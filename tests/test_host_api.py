@@ -360,3 +360,43 @@ def test_gloo_world2_tally_reduction():
     assert [o[1:3] for o in out] == [(0, 501), (501, 1001)]
     for o in out:
         assert o[3][0][0] == 1001 and o[3][2][1] == 3 and o[4] == 1001
+
+
+def test_fused_plan_is_cached_and_chunks_end_on_compaction_boundaries():
+    """The fused step keeps its state (cadence, pinned feedback buffers) across run_steps calls, and a chunk
+    handed to the C ABI ends where a launch would compact anyway."""
+    s = phys.Simulation(cl_on=False)
+    s.cl_on = True  # plan construction only; nothing is launched
+    upd = phys.UpdateTimeStep(lambda c: 1e-3)
+    kin = phys.newton.NewtonianKinematicsStep()
+    sc = phys.light.ScatterIsotropicStep(A=1e-3, n=1e-3)
+    esc = phys.light.EscapeSphereStep(3e6)
+    s.add_step(0, upd)
+    s.add_step(1, kin)
+    s.add_step(2, sc)
+    s.add_step(3, esc)
+    p1, p2 = s._plan(), s._plan()
+    assert p1 is p2 and isinstance(p1[1], fused.FusedPhotonStep) and p1[1].retires
+    s.add_step(4, phys.light.ScatterSignMeasureStep(None))
+    p3 = s._plan()
+    assert p3 is not p1 and len(p3) == 2 and p3[1].measures
+    f = p3[1]
+    assert s.feedback_every == 64 and f.cadence == 4
+    for idx, want in ((0, 64), (5, 63), (7, 61), (8, 64)):  # (4 - idx % 4) + 60
+        s.step_index = idx
+        assert f.chunk_steps(s) == want and (idx + want) % 4 == 0
+    s.compact_cadence = 1
+    assert f.chunk_steps(s) == 64
+    s.compact_cadence, s.feedback_every = None, 8
+    f.cadence = 8
+    s.step_index = 3
+    assert f.chunk_steps(s) == 8  # m >= feedback_every: the chunk is feedback_every long
+    # pipelines that never retire photons take whole chunks
+    t = phys.Simulation(cl_on=False)
+    t.cl_on = True
+    t.add_step(0, upd)
+    t.add_step(1, phys.newton.NewtonianKinematicsStep())
+    t.add_step(2, phys.light.ScatterIsotropicStep(A=1e-3, n=1e-3))
+    g = t._plan()[1]
+    assert not g.retires and g.chunk_steps(t) == 64
+    assert kin.chunk_steps(s) == 256 and kin.can_run_many(s)
