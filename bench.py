@@ -461,7 +461,7 @@ def bench_gravity(args, rank, world, local):
         "e2e": None, "gpu_launches": int(ctx.launches - l0),
         "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
                      "peak_source": "FFMA-only micro-kernel measured in this run (pcl_measure_fp32_peak)",
-                     "kernel": "pcl_k_gravity<4>", "algorithmic_flops": "20 FLOP per pairwise interaction", "per_rank": True},
+                     "kernel": "pcl_k_gravity_x2<2,128,512>", "algorithmic_flops": "20 FLOP per pairwise interaction", "per_rank": True},
         "clocks": clocks.summary(),
     }
 

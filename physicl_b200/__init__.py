@@ -177,7 +177,7 @@ class Simulation(threading.Thread):
         # queued in ~0.1 ms of host time, so the GPU keeps running through host-side hiccups (other ranks' threads,
         # the scheduler); the retirement policy needs no finer feedback (physicl_b200/fused.py)
         self.feedback_every = 64
-        self.compact_cadence = None  # every m-th timestep retires-and-compacts; None = adaptive
+        self.compact_cadence = None  # survivors are compacted after every m-th timestep; None = chosen by the fused step
         for attr, val in kwargs.items():
             setattr(self, attr, val)
         self.dt = Measurement(np.double(0), "s**1")

@@ -53,7 +53,7 @@ class FusedPhotonStep(physicl.Step):
         self.retires = bool(escape or scatter.mode & _capi.SCATTER_DELETE)
         # variable-density steps run a run-time compiled kernel (light.py:295-299), in place only
         self.varn = bool(getattr(scatter, "variable_n", False))
-        self.cadence = 4  # m: every m-th timestep compacts; adapted from lagged tally feedback
+        self.cadence = 4  # m: timesteps per compacting launch (4 or 8, from lagged tally feedback)
         self._fb = []  # pending feedback: (event, pinned int64[18], buffer index at enqueue time)
         self._fb_pool = []
 

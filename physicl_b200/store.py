@@ -11,9 +11,9 @@ A store holds up to two homogeneous groups, because the reference's scatter step
 (newton.py:14, light.py:423): ``photon`` and ``object``.
 
 Retirement.  A retired photon (absorbed, escaped) is a slot whose x is NaN.  Pipelines that retire
-photons run on a PING-PONG pair of plane sets: most timesteps update in place, and every m-th
-timestep is a retire-and-compact step that writes the survivors densely into the partner set
-(``pcl_photon_step_compact``).  The number of valid slots then lives on the device (``n_dev``) and
+photons run on a PING-PONG pair of plane sets: a launch advances the photons m timesteps in registers
+and then writes the survivors densely into the partner set (``pcl_photon_steps_pp``; one timestep at
+a time: ``pcl_photon_step_compact``).  The number of valid slots then lives on the device (``n_dev``) and
 kernels read it there, so the stepping loop never waits for the host; ``n`` on the host is an upper
 bound until ``sync_n`` is called.
 """
