@@ -273,7 +273,15 @@ class Simulation(threading.Thread):
                 if kind == "photon":
                     E = np.array([np.nan if getattr(o, "E", None) is None else float(np.asarray(o.E)) for o in mine])
                 a = np.array([np.asarray(o.a, np.float64) for o in mine]).reshape(-1, 3).T
-                store.add_group(kind, r, v, E=E, a=a if np.any(a) else None, id_base=lo, host_objs=mine)
+                g = store.add_group(kind, r, v, E=E, a=a if np.any(a) else None, id_base=lo, host_objs=mine)
+                # Object.dr (physicl/__init__.py:391) is state too: measure steps that run after a host step read the
+                # displacement of this timestep (light.py:385-399), so it travels with the rebuild
+                dr = np.array([np.asarray(o.dr, np.float64) for o in mine]).reshape(-1, 3).T
+                if np.any(dr):
+                    for q, nm in enumerate(("dx", "dy", "dz")):
+                        g.upload(nm, dr[q])
+                if any(hasattr(o, "nscat") for o in mine):
+                    g.upload("nscat", np.array([int(getattr(o, "nscat", 0)) for o in mine], np.uint32))
         for kind, p in (self._pending or {}).items():
             if hasattr(p["r"], "is_cuda") and p["r"].is_cuda:  # device tensors: this rank's block as is
                 store.add_group(kind, p["r"], p["v"], E=p["E"], a=p["a"], id_base=int(p["id_base"] or 0),

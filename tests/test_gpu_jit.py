@@ -326,3 +326,80 @@ def test_user_program_inside_a_step_next_to_device_steps():
         want = np.float32(z0) + (k + 1) * np.float32(vz0) * np.float32(0.001) + 5.0
         assert np.allclose(row["h"], want, rtol=0, atol=1e-5)
         assert np.array_equal(row["up"], (np.float32(vz0) > 0).astype(np.int32))
+
+
+def test_a_step_written_like_the_references_own_delete_step(golden):
+    """A user step that declares its kernel through CLInput / CLOutput / CLProgram the way the reference's
+    ScatterDeleteStep does (physicl/light.py:231-260: type filter, dr inputs, one np.random draw per photon,
+    swapped constants, int flags, sim.remove_obj per flagged photon), between the device kinematics step and a
+    device measure step.  With the reference's seed the run reproduces the reference's run: same flags, same
+    survivors in the same order, same plane-crossing rows (tests/golden/delete.npz)."""
+    import physicl_b200 as physicl
+    import physicl_b200.light
+    import physicl_b200.newton
+
+    gd = golden("delete")
+
+    class UserDeleteStep(physicl.Step):
+        def __init__(self, n, A):
+            self.n, self.A, self.built, self.flags = n, A, False, []
+
+        def run(self, sim):
+            if not self.built:
+                skip = physicl.CLInput(name="photon_check", type="obj_action",
+                                       code="if type(obj) != physicl.light.PhotonObject:\n \t\t continue")
+                d0, d1, d2 = [physicl.CLInput(name="d" + str(x), type="obj", obj_attr="dr[" + str(x) + "]") for x in range(3)]
+                rand = physicl.CLInput(name="rand", type="obj_def", obj_def="np.random.random()")
+                A_ = physicl.CLInput(name="A", type="const", const_value=str(self.n))
+                n_ = physicl.CLInput(name="n", type="const", const_value=str(self.A))
+                pht = physicl.CLInput(name="pht", type="obj_track", obj_track="obj")
+                res = physicl.CLOutput(name="res", ctype="int")
+                kernel = """
+                    int gid = get_global_id(0);
+                    double norm = sqrt(pow(d0[gid], 2) + pow(d1[gid], 2) + pow(d2[gid], 2));
+                    double pcoll = A * n * norm;
+                    if (pcoll >= rand[gid]){
+                        res[gid] = 1;
+                    } else {
+                        res[gid] = 0;
+                    }
+                """
+                self.prog = physicl.CLProgram(sim, "test", kernel)
+                self.prog.prep_metadata = [skip, d0, d1, d2, rand, pht, A_, n_]
+                self.prog.output_metadata = [res]
+                self.prog.build_kernel()
+                self.built = True
+            out = self.prog.run()
+            self.flags.append(out["res"].copy())
+            for idx, x in enumerate(out["res"]):
+                if x == 1:
+                    sim.remove_obj(self.prog.pht[idx])
+
+    np.random.seed(int(gd["seed"]))
+    nsteps = int(gd["nsteps"])
+    sim = physicl.Simulation(bounds=np.array([1000, 1000, 1000]), cl_on=True, exit=lambda c: len(c.ts) >= nsteps)
+    for i in range(int(gd["N"])):
+        p = physicl.light.PhotonObject(s=np.zeros(3), v=np.array([physicl.light.c, 0, 0], dtype=np.double), E=np.double(1))
+        p.gid = i
+        sim.add_obj(p)
+    step = UserDeleteStep(np.double(gd["n"]), np.double(gd["A"]))
+    plane = physicl.light.ScatterMeasureStep(None, True, [np.array(gd["planes"][0])])
+    survivors = []
+
+    class Snapshot(physicl.Step):
+        def run(self, sim):
+            survivors.append([o.gid for o in sim.objects])
+
+    sim.add_step(0, physicl.UpdateTimeStep(lambda s: np.double(float(gd["dt"]))))
+    sim.add_step(1, physicl.newton.NewtonianKinematicsStep())
+    sim.add_step(2, step)
+    sim.add_step(3, plane)
+    sim.add_step(4, Snapshot())
+    sim.start()
+    sim.join()
+    assert len(step.flags) == nsteps
+    for s in range(nsteps):
+        assert np.array_equal(step.flags[s], gd["s%d_flags" % s]), s
+        assert survivors[s] == list(gd["s%d_gid" % s]), s
+    assert np.array_equal(np.array(plane.data)[:, 1:], gd["plane_rows"][:, 1:])
+    assert 0 < len(sim.objects) < int(gd["N"])
