@@ -408,8 +408,11 @@ def bench_kinematics(args, rank, world, local, n, accel, graph):
                    "l2": "state %d MB per GPU %s" % (n * (48 if accel else 36) // 10 ** 6,
                                                       "fits the 126 MB L2: HBM fraction is optimistic" if n * 48 < 120e6 else "> L2")},
         "e2e": None, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": "pcl_k_kinematics",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read + write of one launch over 64 Mi particles with a planes, ncu --set full
+                     # (profiles/r1_ncu_full_kinematics_step.csv; the fused launch moves the same 4.78 GB per launch)
+                     "traffic": 4.777e9 if (accel and n == 64 * 2 ** 20) else None,
+                     "peak_source": peak_src, "kernel": "pcl_k_kinematics<1,1>" if accel else "pcl_k_kinematics<0,1>",
                      "algorithmic_bytes": ("%d B per particle per LAUNCH (timesteps fused in registers: one state round trip per "
                                            "launch; %d B per particle-step when stepped one launch per timestep)" % (bpp, bpp))
                      if graph else "%d B per particle-step" % bpp,
