@@ -249,11 +249,16 @@ __device__ __forceinline__ void pcl_tally_to_shared(const uint32_t (&cnt)[NC], u
     }
 }
 
-#ifndef PCL_MULTI_MINB
-#define PCL_MULTI_MINB PCL_PHOTON_MINB
+// resident CTAs per SM asked of ptxas: the compacting form gains ~5 % from a fourth CTA (64 registers, no
+// spills in the forms the bulk path uses), the in-place form loses ~6 % with it (measured on B200)
+#ifndef PCL_MULTI_MINB_COMPACT
+#define PCL_MULTI_MINB_COMPACT 4
+#endif
+#ifndef PCL_MULTI_MINB_INPLACE
+#define PCL_MULTI_MINB_INPLACE PCL_PHOTON_MINB
 #endif
 template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
-__global__ void __launch_bounds__(PCL_BLOCK, PCL_MULTI_MINB)
+__global__ void __launch_bounds__(PCL_BLOCK, COMPACT ? PCL_MULTI_MINB_COMPACT : PCL_MULTI_MINB_INPLACE)
 pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
     constexpr int NC = PL ? C_N : C_PLANE0;
     constexpr int NST = COMPACT ? (WAVE ? 9 : 8) : 1;  // staged planes: x y z vx vy vz id nscat [e]
