@@ -340,9 +340,9 @@ def bench_photon_sphere(args, rank, world, local):
                    "escaped_in_window": int(hist[-args.steps:].sum()) if len(hist) else 0},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 881.8e6, "traffic_note": "dram__bytes_read+write of one pcl_k_photon_multi launch advancing 16 Mi "
-                     "photons by 4 timesteps (profiles/r1_ncu_full_photon_multi.csv): 13.1 B per photon-step against 39.6 B "
-                     "algorithmic, because the timesteps are fused in registers; the kernel is issue-bound (70 % of peak issue rate), "
+                     "traffic": 815.8e6, "traffic_note": "dram__bytes_read+write of one pcl_k_photon_multi launch advancing 16 Mi "
+                     "photons by 5 timesteps (profiles/r1_ncu_full_photon_multi.csv): 9.7 B per photon-step against 39.6 B "
+                     "algorithmic, because the timesteps are fused in registers; the kernel is issue-bound (75 % of peak issue rate), "
                      "not DRAM-bound",
                      "peak_source": peak_src, "kernel": "pcl_k_photon_multi<0,0,0,0,1>",
                      "algorithmic_bytes": "(36 + 12 f) B per live photon-step, f = scattered fraction (SURVEY.md 8d), summed over the "
