@@ -400,3 +400,24 @@ def test_fused_plan_is_cached_and_chunks_end_on_compaction_boundaries():
     g = t._plan()[1]
     assert not g.retires and g.chunk_steps(t) == 64
     assert kin.chunk_steps(s) == 256 and kin.can_run_many(s)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/physicl_b200.h is a C header (no C++ constructs): a C99 translation unit that takes the address of
+    every declared entry point compiles with gcc and links against the shared library."""
+    import subprocess
+
+    hdr = open(os.path.join(REPO, "include", "physicl_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(pcl_[a-z0-9_]+)\s*\(", hdr)) - {"pcl_ctx"})
+    assert len(names) >= 30
+    src = tmp_path / "abi.c"
+    body = "\n".join("    p[%d] = (void (*)(void))%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "physicl_b200.h"\n#include <stdio.h>\nint main(void) {\n    void (*p[%d])(void);\n%s\n'
+                   '    printf("%%d %%d\\n", %d, pcl_abi_version());\n    return p[0] == 0;\n}\n' % (len(names), body, len(names)))
+    exe = tmp_path / "abi"
+    lib = os.path.join(REPO, "physicl_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"), str(src),
+                        "-o", str(exe), "-L", lib, "-l:libphysicl_b200.so", "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == [str(len(names)), "1"]
