@@ -156,7 +156,10 @@ class CLProgram:
         import physicl_b200
         import physicl_b200.light  # noqa: F401  (user code says physicl.light.PhotonObject)
 
-        env = {"physicl": physicl_b200, "physicl_b200": physicl_b200, "np": np, "self": self}
+        # the reference executes the generated text inside its own module (physicl/__init__.py:631-635), so user code
+        # sees that module's names
+        env = {"physicl": physicl_b200, "physicl_b200": physicl_b200, "np": np, "self": self,
+               "Measurement": physicl_b200.Measurement, "Object": physicl_b200.Object}
         initial, loop, other = "", "for obj in self.sim.objects:\n\tpass", ""
         for item in self.prep_metadata:
             if item.type in ("obj", "obj_def", "obj_track"):
