@@ -295,6 +295,9 @@ class Simulation(threading.Thread):
                             E=None if p["E"] is None else np.asarray(p["E"])[sl],
                             a=None if p["a"] is None else np.asarray(p["a"]).reshape(3, -1)[:, sl],
                             id_base=lo, track_nscat=p["track_nscat"])
+        # the device store is the only authority for bulk particles from here on: a later rebuild pulls them back as
+        # objects (they must not be ingested a second time from the caller's original arrays)
+        self._pending = None
         self.store = store
         self._host_dirty = False
         self._device_dirty = False

@@ -52,19 +52,28 @@ void pcl_hostpipe_destroy(pcl_ctx *ctx) {
     ctx->pipe = nullptr;
 }
 
-static int pipe_prepare(pcl_ctx *ctx, uint64_t chunk) {
-    if (ctx->pipe && ctx->pipe->chunk == chunk) return 0;
-    pcl_hostpipe_destroy(ctx);
-    pcl_hostpipe *hp = (pcl_hostpipe *)calloc(1, sizeof(pcl_hostpipe));
-    PCL_REQUIRE(ctx, hp != nullptr, "out of host memory");
-    ctx->pipe = hp;
-    hp->chunk = chunk;
+static int pipe_alloc(pcl_ctx *ctx, pcl_hostpipe *hp, uint64_t chunk) {
     for (int s = 0; s < PIPE_SLOTS; ++s) {
         PCL_CUDA(ctx, cudaStreamCreateWithFlags(&hp->stream[s], cudaStreamNonBlocking));
         for (int q = 0; q < 12; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->buf[s][q], chunk * sizeof(float)));
     }
     PCL_CUDA(ctx, cudaMalloc(&hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t)));
     PCL_CUDA(ctx, cudaMallocHost(&hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t)));
+    return 0;
+}
+
+static int pipe_prepare(pcl_ctx *ctx, uint64_t chunk) {
+    if (ctx->pipe && ctx->pipe->chunk == chunk) return 0;
+    pcl_hostpipe_destroy(ctx);
+    pcl_hostpipe *hp = (pcl_hostpipe *)calloc(1, sizeof(pcl_hostpipe));
+    PCL_REQUIRE(ctx, hp != nullptr, "out of host memory");
+    ctx->pipe = hp;
+    int rc = pipe_alloc(ctx, hp, chunk);
+    if (rc) {  // a half-built pipe must not be found (and reused with null buffers) by the next call
+        pcl_hostpipe_destroy(ctx);
+        return rc;
+    }
+    hp->chunk = chunk;
     return 0;
 }
 
@@ -173,7 +182,7 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
     const uint64_t nchunks = (host->n + chunk - 1) / chunk;
     uint64_t out_off = 0;
     // planes that travel: index into buf/out
-    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, wave ? host->e : nullptr,
+    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->e,
                         (float *)host->id, (float *)host->nscat};
     auto complete = [&](uint64_t c) -> int {  // read the survivor count of chunk c, queue its D2H copies
         const int s = (int)(c % PIPE_SLOTS);
@@ -201,7 +210,7 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
             if (hplane[q]) PCL_CUDA(ctx, cudaMemcpyAsync(in[q], hplane[q] + off, m * sizeof(float), cudaMemcpyHostToDevice, st));
         src.x = in[0]; src.y = in[1]; src.z = in[2]; src.vx = in[3]; src.vy = in[4]; src.vz = in[5];
         dst.x = ou[0]; dst.y = ou[1]; dst.z = ou[2]; dst.vx = ou[3]; dst.vy = ou[4]; dst.vz = ou[5];
-        if (wave) { src.e = in[6]; dst.e = ou[6]; }
+        if (host->e) { src.e = in[6]; dst.e = ou[6]; }
         src.id = (uint32_t *)in[7]; dst.id = (uint32_t *)ou[7];
         if (host->nscat) { src.nscat = (uint32_t *)in[8]; dst.nscat = (uint32_t *)ou[8]; }
         rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, 1, false);
@@ -254,7 +263,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
     PCL_REQUIRE(ctx, rng->u_rand == nullptr, "the compacting host step draws from Philox");
     const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH;
     if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
-    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, wave ? host->e : nullptr,
+    float *hplane[9] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->e,
                         (float *)host->id, (float *)host->nscat};
     float *dplane[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool mapped = true;
@@ -305,7 +314,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
         src.n = m;
         src.id_base = host->id_base;
         src.x = in[0]; src.y = in[1]; src.z = in[2]; src.vx = in[3]; src.vy = in[4]; src.vz = in[5];
-        if (wave) src.e = in[6];
+        if (host->e) src.e = in[6];
         src.id = (uint32_t *)in[7];
         if (host->nscat) src.nscat = (uint32_t *)in[8];
         pcl_soa d = dst;

@@ -268,7 +268,7 @@ template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
 __global__ void __launch_bounds__(PCL_BLOCK, COMPACT ? PCL_MULTI_MINB_COMPACT : PCL_MULTI_MINB_INPLACE)
 pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
     constexpr int NC = PL ? C_N : C_PLANE0;
-    constexpr int NST = COMPACT ? (WAVE ? 9 : 8) : 1;  // staged planes: x y z vx vy vz id nscat [e]
+    constexpr int NST = COMPACT ? 9 : 1;  // staged planes: x y z vx vy vz id nscat e
     __shared__ float s_stage[NST][COMPACT ? PCL_BLOCK * 4 : 1];
     __shared__ uint32_t s_warp[PCL_WARPS];
     __shared__ unsigned long long s_base;
@@ -278,6 +278,9 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
     const uint64_t n = pcl_valid_slots(s);
     const uint64_t ntiles = (n + PCL_BLOCK * 4 - 1) / (PCL_BLOCK * 4);
     const bool has_id = s.id != nullptr;
+    // the e plane travels with the survivors whenever both sides have one, also when the law does not read it
+    // (a photon keeps its energy through delete scattering and the escape sphere: light.py:34)
+    const bool carry_e = COMPACT && !WAVE && s.e != nullptr && d.e != nullptr;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t i = (tile * PCL_BLOCK + threadIdx.x) * 4;
@@ -381,6 +384,15 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
         uint32_t keep = 0u;
 #pragma unroll
         for (int l = 0; l < 4; ++l) keep |= (pcl_f4(x, l) == pcl_f4(x, l)) ? (1u << l) : 0u;
+        if (carry_e) {  // loaded only now: the timestep loop above does not hold it in registers
+            if (full) {
+                e = pcl_ld4(s.e + i);
+            } else {
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+                    if (i + l < n) pcl_f4(e, l) = s.e[i + l];
+            }
+        }
         // tile-local rank of this thread's first survivor: shuffle scan inside the warp, warp totals
         // through shared memory
         const uint32_t c = __popc(keep);
@@ -413,7 +425,7 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             s_stage[5][rk] = pcl_f4(vz, l);
             s_stage[6][rk] = __uint_as_float(pcl_u4(id, l));
             s_stage[7][rk] = __uint_as_float(pcl_u4(nsc, l));
-            if (WAVE) s_stage[NST - 1][rk] = pcl_f4(e, l);
+            if (WAVE || carry_e) s_stage[NST - 1][rk] = pcl_f4(e, l);
             ++rk;
         }
         __syncthreads();
@@ -434,7 +446,7 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             d.vz[o] = s_stage[5][q];
             d.id[o] = __float_as_uint(s_stage[6][q]);
             if (s.nscat) d.nscat[o] = __float_as_uint(s_stage[7][q]);
-            if (WAVE) d.e[o] = s_stage[NST - 1][q];
+            if (WAVE || carry_e) d.e[o] = s_stage[NST - 1][q];
         }
         __syncthreads();  // the stage and s_warp are rewritten by the next tile
     }
@@ -693,7 +705,7 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
         PCL_REQUIRE(ctx, dst->x && dst->y && dst->z && dst->vx && dst->vy && dst->vz && dst->id,
                     "dst needs r, v and id planes");
         PCL_REQUIRE(ctx, dst->x != p->x, "the compacting step writes out of place");
-        if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, dst->e != nullptr, "dst needs the e plane");
+        if (p->e) PCL_REQUIRE(ctx, dst->e != nullptr, "dst needs the e plane (energies travel with the survivors)");
         if (p->nscat) PCL_REQUIRE(ctx, dst->nscat != nullptr, "dst needs the nscat plane");
         if (p->n == 0) {
             if (!keep_count) PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));

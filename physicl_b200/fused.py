@@ -59,7 +59,10 @@ class FusedPhotonStep(physicl.Step):
 
     # ---- helpers --------------------------------------------------------------------------------
     def _fallback(self, st):
-        return "object" in st.groups or st.group("photon") is None or self._multi_plane
+        g = st.group("photon")
+        # photons that carry acceleration planes: the retire-and-compact kernel does not move those, the stand-alone
+        # steps + pcl_compact do
+        return "object" in st.groups or g is None or self._multi_plane or (self.retires and "ax" in g.planes)
 
     def can_run_many(self, sim):
         st = sim.device_store()

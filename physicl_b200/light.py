@@ -229,6 +229,7 @@ class _ScatterBase(physicl.Step):
         if "dx" not in g.planes:
             raise RuntimeError("%s needs the displacement of this timestep: add NewtonianKinematicsStep before it "
                                "(reference pipelines do: test/test_light.py:33-34)" % type(self).__name__)
+        st.sync_n("photon")  # stand-alone kernels take the exact slot count from the host
         sp = self.scatter_params(g)
         rng, keep = self.rng_params(sim, st, g)
         row = st.new_row()
@@ -309,6 +310,7 @@ class EscapeSphereStep(physicl.Step):
         g = st.group("photon")
         if g is None or g.n == 0:
             return
+        st.sync_n("photon")
         row = st.new_row()
         soa = g.soa()
         sim.cl_ctx.call("pcl_escape", st.stream(), C.byref(soa), C.c_float(self.R * self.R), st.row_ptr())
@@ -373,7 +375,8 @@ class _DeviceMeasureStep(physicl.MeasureStep):
         st = sim.device_store()
         row = st.new_row()
         pl = _capi.make_planes(self._planes())
-        for g in st.groups.values():
+        for kind, g in st.groups.items():
+            st.sync_n(kind)
             if g.n == 0:
                 continue
             if pl.count:

@@ -44,7 +44,8 @@ class NewtonianKinematicsStep(physicl.Step):
         au = None
         if self.a_uniform is not None:
             au = self.a_uniform.ctypes.data_as(C.POINTER(C.c_float))
-        for g in st.groups.values():
+        for kind, g in st.groups.items():
+            st.sync_n(kind)  # after a device-side compaction the exact slot count lives on the device
             if self.write_dr:
                 g.ensure("dx", "dy", "dz")
             if self.accel and self.a_uniform is None and "ax" not in g.planes:
@@ -91,7 +92,7 @@ class NewtonianGravityStep(physicl.Step):
         posm[:, 0], posm[:, 1], posm[:, 2] = g.planes["x"][:n], g.planes["y"][:n], g.planes["z"][:n]
         posm[:, 3] = torch.from_numpy(m).to(st.device)
         acc = torch.zeros((3, n), dtype=torch.float32, device=st.device)
-        self._state = dict(posm=posm, acc=acc, n=n, all=None)
+        self._state = dict(posm=posm, acc=acc, n=n, all=None, store=st)
         if sim.shard:
             from .dist import GravityExchange
 
@@ -100,8 +101,10 @@ class NewtonianGravityStep(physicl.Step):
 
     def run(self, sim):
         st = sim.device_store()
-        s = self._state or self._setup(sim)
+        s = self._state
         g = st.group("object")
+        if s is None or s["store"] is not st or (g is not None and s["n"] != g.n):
+            s = self._setup(sim)  # first use, or the store was rebuilt (host step, changed object list): repack
         n, posm, acc = s["n"], s["posm"], s["acc"]
         ctx, stream = sim.cl_ctx, st.stream()
         p = lambda t: C.c_void_p(t.data_ptr())

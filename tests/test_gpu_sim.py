@@ -525,3 +525,151 @@ def test_presentation_example_2_runs_with_only_the_import_changed():
     dirs = np.diff(path, axis=1) / (c * dt)
     others = np.delete(np.arange(300), 5)
     assert np.all(np.abs(dirs[others, 0, 0] - 1.0) > 1e-6)
+
+
+# ---- regressions for the round-1 advisor findings ---------------------------------------------------
+def _energy_photons(n):
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    E = 1.0 + np.arange(n, dtype=np.float64) / n  # distinct, exactly representable after the /E0 scaling or not: compare by id
+    return r, v, E
+
+
+@pytest.mark.parametrize("law", ["delete", "escape"])
+def test_energies_survive_device_compaction(law):
+    """A photon keeps its E through delete scattering / the escape sphere (light.py:34): the compacting
+    kernel must move the e plane with the survivors even though the law does not read it."""
+    n, steps = 50000, 9
+    r, v, E = _energy_photons(n)
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= steps, seed=11)
+    x.add_particles(r, v, E=E)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    if law == "delete":
+        x.add_step(2, phys.light.ScatterDeleteStep(np.double(2e-4), np.double(1e-3)))
+    else:
+        x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+        x.add_step(3, phys.light.EscapeSphereStep(1.2e6))
+    x.add_step(4, phys.light.ScatterSignMeasureStep(None, True))
+    x.run_steps(steps)
+    assert x.store.compactions > 0
+    snap = x.store.snapshot("photon")
+    assert 0 < snap["id"].size < n
+    e0 = x.store.group("photon").e0
+    want = (E / e0).astype(np.float32).astype(np.float64) * e0
+    assert np.array_equal(snap["E"], want[snap["id"]])
+    # ... and in the objects pulled back to the host
+    objs = list(x.objects)
+    assert len(objs) == snap["id"].size
+    assert np.array_equal(np.array([float(o.E) for o in objs]), want[snap["id"]])
+
+
+def test_host_compact_step_carries_energies():
+    """pcl_photon_step_host_compact moves host->e with the survivors when the law is not wavelength-dependent."""
+    import ctypes as C
+
+    ctx = _capi.Context(0)
+    n = 40000
+    host = {k: torch.zeros(n, dtype=torch.float32).pin_memory() for k in ("x", "y", "z", "vx", "vy", "vz")}
+    host["vx"].fill_(float(phys.light.c))
+    host["e"] = (1.0 + torch.arange(n, dtype=torch.float32) / n).pin_memory()
+    e_by_id = host["e"].clone().numpy()
+    host["id"] = torch.arange(n, dtype=torch.int32).pin_memory()
+    soa = _capi.Soa()
+    for k, t in host.items():
+        setattr(soa, k, t.data_ptr())
+    soa.n = n
+    sp = _capi.ScatterParams(k=1e-6, c=float(phys.light.c), mode=_capi.SCATTER_DELETE)
+    pl = _capi.make_planes([])
+    row = np.zeros(_capi.TALLY_COLS, np.int64)
+    n_out = C.c_uint64(0)
+    for s in range(3):
+        rg = _capi.Rng(seed=3, step=s)
+        ctx.call("pcl_photon_step_host_compact", C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0),
+                 C.byref(pl), row.ctypes.data_as(C.c_void_p), C.c_uint64(8192), C.byref(n_out))
+        soa.n = n_out.value
+    m = n_out.value
+    assert 0 < m < n
+    ids = host["id"].numpy()[:m].view(np.uint32)
+    assert np.array_equal(host["e"].numpy()[:m], e_by_id[ids])
+
+
+def test_bulk_particles_are_ingested_once():
+    """add_particles data must not come back a second time when the store is rebuilt (host measure step, add_obj)."""
+    n = 3000
+    r, v, E = _energy_photons(n)
+
+    class CountStep(phys.MeasureStep):  # a host step: walks sim.objects like the reference's measure steps do
+        def run(self, sim):
+            self.data.append(sum(1 for _ in sim.objects))
+
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 6, seed=2)
+    x.add_particles(r, v, E=E)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterDeleteStep(np.double(1e-3), np.double(1e-3)))
+    cnt = CountStep()
+    x.add_step(3, cnt)
+    x.start()
+    x.join()
+    assert cnt.data[0] < n and all(b <= a for a, b in zip(cnt.data, cnt.data[1:]))
+    before = len(x.objects)
+    x.add_obj(phys.light.PhotonObject(E=np.double(1), v=np.array([phys.light.c, 0, 0], dtype=np.double)))
+    x.device_store()
+    assert len(x.objects) == before + 1
+    # every photon dies, then the store is rebuilt: the original particles must stay gone
+    y = phys.Simulation(cl_on=True, exit=lambda c: len(c.objects) == 0, seed=2)
+    y.add_particles(r, v, E=E)
+    y.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    y.add_step(1, phys.newton.NewtonianKinematicsStep())
+    y.add_step(2, phys.light.ScatterDeleteStep(np.double(1.0), np.double(1.0)))
+    y.start()
+    y.join()
+    assert len(list(y.objects)) == 0
+    y._host_dirty = True
+    assert y.device_store().n_slots == 0
+
+
+def test_unfused_steps_after_a_device_compaction():
+    """Stand-alone device steps (tally before kinematics, escape not adjacent to scatter) keep working once the
+    fused retiring step has compacted on the device (the slot count then lives in n_dev)."""
+    n = 40000
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 10, seed=9)
+    x.add_particles(r, v)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    first = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(1, first)  # measure step BEFORE the kinematics step: runs unfused
+    x.add_step(2, phys.newton.NewtonianKinematicsStep())
+    x.add_step(3, phys.light.ScatterDeleteStep(np.double(2e-4), np.double(1e-3)))
+    after = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(4, after)
+    x.add_step(5, phys.light.EscapeSphereStep(2.0e6))  # not adjacent to the scatter step: unfused
+    x.start()
+    x.join()
+    a, b = np.array(first.data), np.array(after.data)
+    assert a.shape[0] == b.shape[0] == 10
+    assert a[0, 1] == n
+    assert np.array_equal(a[1:7, 1], b[:6, 1])  # nothing reaches R = 2e6 before step 7: counts carry over
+    assert b[-1, 1] < n
+
+
+def test_gravity_step_sees_a_rebuilt_store():
+    n = 512
+    rng = np.random.default_rng(3)
+    pos, vel = rng.normal(size=(3, n)), np.zeros((3, n))
+    x = phys.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 2)
+    x.add_particles(pos, vel, kind="object")
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+    grav = phys.newton.NewtonianGravityStep(G=1.0, eps2=1e-2, masses=np.full(n, 1.0 / n, np.float32))
+    x.add_step(1, grav)
+    x.run_steps(2)
+    objs = list(x.objects)  # pull to host, edit, rebuild
+    objs[0].r = phys.Measurement([50.0, 0.0, 0.0], "m**1")
+    x._host_dirty = True
+    x.run_steps(1)
+    snap = x.store.snapshot("object")
+    assert abs(snap["x"][0] - 50.0) < 1.0  # the edit was not overwritten by a stale packed array
