@@ -118,6 +118,10 @@ int pcl_device_info(pcl_ctx *ctx, char *name, int name_len, int *sm_count, uint6
 /* kernels launched through this ctx so far (bench.py "gpu_launches") */
 uint64_t pcl_launch_count(pcl_ctx *ctx);
 int pcl_stream_sync(pcl_ctx *ctx, uintptr_t stream);
+/* Timing aid (no reference counterpart): work queued on `stream` after this call waits ON THE DEVICE
+ * until *flag_host (4 bytes of page-locked, mapped host memory) is non-zero, at most timeout_ms
+ * (capped at 10 s).  bench.py queues a timed region behind it, so that CUDA events bracket GPU work only. */
+int pcl_stream_gate(pcl_ctx *ctx, uintptr_t stream, const uint32_t *flag_host, uint32_t timeout_ms);
 
 /* ---- steps --------------------------------------------------------------------------------- */
 /* NewtonianKinematicsStep.run (physicl/newton.py:14-16): dr = v*dt; r += dr.
@@ -234,6 +238,14 @@ int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt,
                                  const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                                  const pcl_planes *planes, int64_t *tally_row_host, uint64_t chunk,
                                  uint64_t *n_out_host);
+/* nsteps (1..8) timesteps per host round trip, for callers that do not look at the particles between
+ * those timesteps (Simulation.run with no host step in the list, physicl/__init__.py:512-516): a chunk is
+ * uploaded once, advanced nsteps timesteps by one launch and its survivors come back.
+ * tally_rows_host: int64[nsteps][PCL_TALLY_COLS], one row per timestep. */
+int pcl_photon_steps_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt,
+                                  const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
+                                  const pcl_planes *planes, int64_t *tally_rows_host, uint64_t chunk,
+                                  uint32_t nsteps, uint64_t *n_out_host);
 int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes);
 int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
 

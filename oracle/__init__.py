@@ -168,6 +168,13 @@ def kinematics_f64(r, v, dt):
     return dr
 
 
+def kinematics_accel_f64(r, v, a, dr, dt):
+    """NEW law (v += a dt; dr = v dt; r += dr) in double; r, v, a, dr: (3, N) float64, updated in place."""
+    lib().orc_kinematics_accel_f64(C.c_uint64(r.shape[1]), *[_p(r[i], np.float64) for i in range(3)],
+                                   *[_p(v[i], np.float64) for i in range(3)], *[_p(a[i], np.float64) for i in range(3)],
+                                   *[_p(dr[i], np.float64) for i in range(3)], C.c_double(dt))
+
+
 def scatter_sphere_f64(dr, rtheta, rphi, rnd, A, n, c, E=None, hc=0.0):
     N = rnd.size
     res = np.full((3, N), np.nan)

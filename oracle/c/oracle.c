@@ -340,6 +340,25 @@ void orc_kinematics_f64(uint64_t n, double *x, double *y, double *z, const doubl
     }
 }
 
+/* NEW (not in the reference, whose Object.a is never read): semi-implicit Euler with per-particle a,
+ * v += a dt; dr = v dt; r += dr -- the law of BASELINE configs[0] / configs[4], in double, for the CPU arm */
+void orc_kinematics_accel_f64(uint64_t n, double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                              const double *ax, const double *ay, const double *az, double *dx, double *dy, double *dz,
+                              double dt) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        vx[i] += ax[i] * dt;
+        vy[i] += ay[i] * dt;
+        vz[i] += az[i] * dt;
+        dx[i] = vx[i] * dt;
+        dy[i] = vy[i] * dt;
+        dz[i] = vz[i] * dt;
+        x[i] += dx[i];
+        y[i] += dy[i];
+        z[i] += dz[i];
+    }
+}
+
 /* light.py:303-315 kernel body: res0 = NAN marks "unaffected"; hc_over applies :300-301 when E given */
 void orc_scatter_sphere_f64(uint64_t n, const double *d0, const double *d1, const double *d2, const double *rtheta,
                             const double *rphi, const double *rnd, double A, double nd, const double *E, double hc,

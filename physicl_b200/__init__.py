@@ -141,7 +141,13 @@ class _ObjectList(list):
         sim = self._sim
         if sim._device_dirty and sim.store is not None:
             return sim._device_live_count()
-        return super().__len__()
+        n = super().__len__()
+        for p in (sim._pending or {}).values():  # bulk particles that have not been uploaded yet
+            r = p["r"]
+            n += int(r.shape[1]) if hasattr(r, "shape") and len(r.shape) == 2 else int(np.asarray(r).reshape(3, -1).shape[1])
+        if sim.store is not None and not sim._host_dirty:  # bulk groups live on the device only
+            n += sum(g.n_live for g in sim.store.groups.values() if g.host_objs is None)
+        return n
 
     def __iter__(self):
         self._sim._pull_objects()

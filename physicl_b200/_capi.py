@@ -17,6 +17,12 @@ TALLY_COLS = 16
 T_ALIVE, T_XP, T_YP, T_ZP, T_SCATTERED, T_ABSORBED, T_ESCAPED, T_LIVE_IN, T_PLANE0 = range(9)
 SCATTER_WAVELENGTH, SCATTER_DELETE = 1, 2
 
+# thread-level SASS instructions executed per live photon-step by the shipped fused kernels (ncu, profiles/README.md);
+# bench.py turns them into the issue-rate roofline of the photon workloads
+PHOTON_INSTR_PER_STEP = 185.0
+PHOTON_INSTR_PER_STEP_WAVE = 185.0
+GRAVITY_KERNEL = "pcl_k_gravity_x2<2,128,512>"
+
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
 
@@ -73,6 +79,7 @@ _PROTOS = {
     "pcl_device_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pcl_launch_count": (C.c_uint64, [C.c_void_p]),
     "pcl_stream_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pcl_stream_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "pcl_kinematics": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_int, _f32p]),
     "pcl_kinematics_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_int, _f32p, C.c_uint32]),
     "pcl_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(ScatterParams), C.POINTER(Rng), C.c_void_p, C.c_void_p]),
@@ -90,6 +97,7 @@ _PROTOS = {
     "pcl_gravity_kick_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcl_photon_step_host": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64]),
     "pcl_photon_step_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pcl_photon_steps_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "pcl_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pcl_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pcl_jit_build": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]),

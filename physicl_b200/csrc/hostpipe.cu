@@ -4,7 +4,8 @@
 // physicl/__init__.py:602-664: cl_array.to_device per input :614, launch :656, .get() per output
 // :659-662), restated for PCIe Gen5 + B200: the shard is cut into chunks, and chunk c's H2D copies,
 // its kernel and its D2H copies are queued on stream c % PIPE_SLOTS, so the two copy engines and
-// the SMs all stay busy.  Bytes over PCIe per photon-step: 24 B up (r, v) + 24 B down (+4 B e up).
+// the SMs all stay busy.  Bytes over PCIe per photon-step: in-place form 24 B up (r, v) + 24 B down
+// (+4 B e up); compacting form 28 B up per photon entering + 28 B down per survivor (r, v, id; +4 B e).
 #include <stdlib.h>
 
 #include "pcl_common.cuh"
@@ -57,8 +58,8 @@ static int pipe_alloc(pcl_ctx *ctx, pcl_hostpipe *hp, uint64_t chunk) {
         PCL_CUDA(ctx, cudaStreamCreateWithFlags(&hp->stream[s], cudaStreamNonBlocking));
         for (int q = 0; q < 12; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->buf[s][q], chunk * sizeof(float)));
     }
-    PCL_CUDA(ctx, cudaMalloc(&hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t)));
-    PCL_CUDA(ctx, cudaMallocHost(&hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t)));
+    PCL_CUDA(ctx, cudaMalloc(&hp->tally_dev, PCL_FUSE_MAX * PCL_TALLY_COLS * sizeof(int64_t)));
+    PCL_CUDA(ctx, cudaMallocHost(&hp->tally_pinned, PCL_FUSE_MAX * PCL_TALLY_COLS * sizeof(int64_t)));
     return 0;
 }
 
@@ -159,7 +160,8 @@ extern "C" int pcl_photon_step_host(pcl_ctx *ctx, const pcl_soa *host, float dt,
 // ---------------------------------------------------------------------------------------------
 static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
                                const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
-                               int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host) {
+                               int64_t *tally_row_host, uint64_t chunk, uint64_t *n_out_host, uint32_t nsteps) {
+    PCL_REQUIRE(ctx, nsteps >= 1 && nsteps <= PCL_FUSE_MAX, "1 to 8 timesteps per host round trip");
     PCL_REQUIRE(ctx, host && sp && rng && tally_row_host && n_out_host, "null argument");
     PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz && host->id,
                 "r, v and id planes are required (ids travel with the photons)");
@@ -177,7 +179,7 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
         for (int s = 0; s < PIPE_SLOTS; ++s)
             for (int q = 0; q < 9; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->out[s][q], chunk * sizeof(float)));
     }
-    PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
+    PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
     PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[0]));
     const uint64_t nchunks = (host->n + chunk - 1) / chunk;
     uint64_t out_off = 0;
@@ -213,7 +215,7 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
         if (host->e) { src.e = in[6]; dst.e = ou[6]; }
         src.id = (uint32_t *)in[7]; dst.id = (uint32_t *)ou[7];
         if (host->nscat) { src.nscat = (uint32_t *)in[8]; dst.nscat = (uint32_t *)ou[8]; }
-        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, 1, false);
+        rc = pcl_photon_step_impl(ctx, st, &src, &dst, dt, sp, rng, escape_r2, planes, hp->tally_dev, hp->cnt_dev + s, nsteps, false);
         if (rc) return rc;
         PCL_CUDA(ctx, cudaMemcpyAsync(hp->cnt_pinned + s, hp->cnt_dev + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (c + 1 >= PIPE_SLOTS) {  // oldest chunk in flight: its slot is needed next
@@ -226,10 +228,22 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
         if (rc) return rc;
     }
     for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
-    PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
-    memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
+    PCL_CUDA(ctx, cudaMemcpy(hp->tally_pinned, hp->tally_dev, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    memcpy(tally_row_host, hp->tally_pinned, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t));
     *n_out_host = out_off;
     return 0;
+}
+
+// nsteps (1..8) timesteps per host round trip: each chunk is uploaded once, advanced nsteps timesteps in registers
+// by ONE launch of the retire-and-compact kernel, and its survivors come back.  For callers that do not need the
+// particles on the host after every single timestep (the reference's Simulation.run with no host step in between,
+// physicl/__init__.py:512-516), PCIe bytes per photon-step drop by nsteps.  tally_rows_host: int64[nsteps][COLS].
+extern "C" int pcl_photon_steps_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt, const pcl_scatter_params *sp,
+                                             const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
+                                             int64_t *tally_rows_host, uint64_t chunk, uint32_t nsteps,
+                                             uint64_t *n_out_host) {
+    PCL_ENTER(ctx);
+    return host_compact_staged(ctx, host, dt, sp, rng, escape_r2, planes, tally_rows_host, chunk, n_out_host, nsteps);
 }
 
 // Is this host plane page-locked and mapped into the device's address space (torch pin_memory(),
@@ -274,7 +288,7 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
     for (int q = 0; q < 9 && mapped; ++q)
         if (hplane[q]) mapped = host_plane_mapped(hplane[q], (void **)&dplane[q]);
     if (!mapped || !zero_copy)
-        return host_compact_staged(ctx, host, dt, sp, rng, escape_r2, planes, tally_row_host, chunk, n_out_host);
+        return host_compact_staged(ctx, host, dt, sp, rng, escape_r2, planes, tally_row_host, chunk, n_out_host, 1);
     if (chunk == 0) chunk = 1u << 20;
     chunk = (chunk + 3) & ~(uint64_t)3;
     int rc = pipe_prepare(ctx, chunk);

@@ -93,6 +93,36 @@ extern "C" int pcl_stream_sync(pcl_ctx *ctx, uintptr_t stream) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stream gate: a one-thread kernel that holds `stream` until a word in mapped host memory becomes
+// non-zero.  A caller queues a whole timed region behind it (event, launches, event) and then opens
+// the gate, so no host-side launch latency lies between the two events.  The wait gives up after
+// timeout_ms, so a host that dies (or blocks on the stream) cannot hang the GPU.
+// ---------------------------------------------------------------------------------------------
+__global__ void pcl_k_gate(const volatile uint32_t *flag, unsigned long long timeout_ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*flag == 0u) {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) break;
+    }
+}
+
+extern "C" int pcl_stream_gate(pcl_ctx *ctx, uintptr_t stream, const uint32_t *flag_host, uint32_t timeout_ms) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, flag_host != nullptr, "null flag");
+    cudaPointerAttributes a;
+    PCL_CUDA(ctx, cudaPointerGetAttributes(&a, flag_host));
+    PCL_REQUIRE(ctx, a.type == cudaMemoryTypeHost && a.devicePointer != nullptr,
+                "the gate flag must live in page-locked, mapped host memory");
+    if (timeout_ms == 0 || timeout_ms > 10000) timeout_ms = 10000;
+    pcl_k_gate<<<1, 1, 0, (cudaStream_t)stream>>>((const volatile uint32_t *)a.devicePointer,
+                                                  (unsigned long long)timeout_ms * 1000000ull);
+    PCL_CUDA(ctx, cudaGetLastError());  // not counted in pcl_launch_count: it does no particle work
+    return 0;
+}
+
 extern "C" int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes) {
     PCL_ENTER(ctx);
     PCL_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));

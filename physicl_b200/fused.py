@@ -130,7 +130,8 @@ class FusedPhotonStep(physicl.Step):
         g = st.group("photon")
         if not self.retires or self.varn:
             st.sync_n("photon")
-        if g.n == 0:
+        if g.n == 0:  # every photon is gone: the measure steps still get their (all-zero) rows, as in the reference
+            self._note(sim, st.new_rows(k), k, ts)
             return
         sp = self.scatter.scatter_params(g)
         rng = _capi.Rng(seed=self.scatter._seed(sim), step=sim.step_index & 0xFFFFFFFF)
@@ -183,6 +184,7 @@ class FusedPhotonStep(physicl.Step):
         # host-drawn uniforms (the reference's np.random stream): in place + stable compaction
         g = st.group("photon")
         if g.n == 0:
+            self._note(sim, st.new_row(), 1, None)
             return
         sp = self.scatter.scatter_params(g)
         rng, keep = self.scatter.rng_params(sim, st, g)

@@ -20,10 +20,16 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["metric"] == "particle-steps/s" and d["value"] > 0
-    assert d["config"]["workload"] == "photon_sphere_16m" and d["steps"] == 2 and d["warmup"] == 3
+    sys.path.insert(0, REPO)
+    import bench
+
+    assert d["config"] == bench.SWEEP_CONFIG  # the same static description the GPU arm prints: same_config
+    assert d["config"]["workload"] == "sweep_1b" and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "strong"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] == len(os.sched_getaffinity(0)) and cb["sample"]
+    ref = cb["reference_e2e"]  # the unmodified reference, end to end (oracle/_ref is built by __graft_entry__.build())
+    assert ref.get("kind") == "reference" and ref["value"] > 0 and ref["cores"] == 1, ref
 
 
 def test_reference_arm_is_silent_on_other_ranks():
@@ -33,7 +39,7 @@ def test_reference_arm_is_silent_on_other_ranks():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_archived_b200_line_carries_the_contract_keys():
+def test_archived_round1_line_carries_the_contract_keys():
     with open(os.path.join(REPO, "profiles", "bench_r1", "bench_default.json")) as f:
         d = json.loads(f.readline())
     assert BASE_KEYS | {"roofline", "clocks", "cpu_baseline"} <= set(d)
