@@ -76,7 +76,22 @@ def philox4x32_10(ctr, key):
     return [int(v) for v in o]
 
 
+def philox2x32_10(ctr, key):
+    c = (C.c_uint32 * 2)(*[int(v) & 0xFFFFFFFF for v in ctr])
+    o = (C.c_uint32 * 2)()
+    lib().orc_philox2x32_10(c, C.c_uint32(int(key) & 0xFFFFFFFF), o)
+    return [int(v) for v in o]
+
+
+def fold_key(seed, id_hi=0, stream=0):
+    f = lib().orc_fold_key
+    f.restype = C.c_uint32
+    return int(f(C.c_uint64(seed), C.c_uint64(id_hi), C.c_uint64(stream)))
+
+
 def philox_uniforms(n, id_base, seed, step, stream=0):
+    """The photon kernels' draws as plain uniforms (u_theta = theta / 2 pi, u_phi = phi / pi, u_rand); stream 1: the
+    emission sampler's Philox4x32 stream."""
     ut = np.empty(n, np.float32)
     up = np.empty(n, np.float32)
     ur = np.empty(n, np.float32)
@@ -85,17 +100,11 @@ def philox_uniforms(n, id_base, seed, step, stream=0):
     return ut, up, ur
 
 
-def sincospi_f32(t):
-    t = np.ascontiguousarray(t, np.float32)
-    s = np.empty_like(t)
-    c = np.empty_like(t)
+def sincos_tab(k, b):
+    """(sin, cos) of table angle 2 pi k / 512 plus remainder b (radians), as the kernels evaluate it."""
     fs, fc = C.c_float(), C.c_float()
-    f = lib().orc_sincospi_f32
-    for i, v in enumerate(t.ravel()):
-        f(C.c_float(float(v)), C.byref(fs), C.byref(fc))
-        s.ravel()[i] = fs.value
-        c.ravel()[i] = fc.value
-    return s, c
+    lib().orc_sincos_tab(C.c_uint32(int(k)), C.c_float(float(b)), C.byref(fs), C.byref(fc))
+    return fs.value, fc.value
 
 
 def _planes(planes):

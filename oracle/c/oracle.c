@@ -11,9 +11,9 @@
  *              unmodified reference (tests/golden/make_golden.py).  Also the CPU baseline that
  *              bench.py times (OpenMP over all host cores).
  *   orc_*_f32  the binary32 twin: the same law evaluated with exactly the operation sequence the
- *              CUDA kernels use (mul, add, explicit fmaf, sqrtf, rintf; no contraction: this file
- *              is compiled with -ffp-contract=off), which makes decisions and integer tallies
- *              bit-identical to the GPU's.
+ *              CUDA kernels use (mul, add, explicit fmaf, floorf, the 512-entry direction table; no
+ *              contraction: this file is compiled with -ffp-contract=off), which makes decisions and
+ *              integer tallies bit-identical to the GPU's.
  * Steps that do not exist in the reference (constant acceleration, escape sphere, gravity, the
  * Philox stream) are marked NEW: their parity is unpinned by the reference; they are checked by
  * invariants in tests/.
@@ -64,17 +64,90 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 static inline float u01(uint32_t r) { return (float)(r >> 8) * 0x1p-24f; }
 
-static inline void draw3(uint64_t gid, uint64_t seed, uint32_t step, uint32_t stream, float *a, float *b, float *c) {
-    uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), step, stream};
-    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t o[4];
-    orc_philox4x32_10(ctr, key, o);
-    *a = u01(o[0]);
-    *b = u01(o[1]);
-    *c = u01(o[2]);
+/* Philox2x32-10 (same paper; Random123 philox2x32_R(10, ...)): one multiply per round, 64 bits per block.
+ * NEW, like every in-kernel draw: the photon steps use it with counter = (low word of the global id, step). */
+void orc_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p;
+        c0 = n0;
+        key += 0x9E3779B9u;
+    }
+    out[0] = c0;
+    out[1] = c1;
 }
 
-/* fill u_theta,u_phi,u_rand[n] with the Philox draws of photons id_base+i at `step` */
+/* 64 -> 32 bit fold of (seed, high word of the global id, stream): splitmix64 finaliser, upper word */
+uint32_t orc_fold_key(uint64_t seed, uint64_t id_hi, uint64_t stream) {
+    uint64_t z = seed ^ (id_hi * 0x9E3779B97F4A7C15ull) ^ (stream << 56);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
+/* One photon's draws for one timestep, in the form the step body consumes them (see pcl_device.cuh):
+ * ur = 24-bit uniform; theta = 2 pi (kt + ft), phi = pi (kp + fp) with kt, kp table indices (multiples of 2 pi/256 and
+ * pi/256) and bt, bp the remainders in radians. */
+typedef struct {
+    float ur;
+    uint32_t kt, kp; /* entry numbers in the 512-entry table */
+    float bt, bp;
+} draw3_t;
+
+#define ORC_TWO_PI_256 0x1.921fb6p-6f
+#define ORC_PI_256 0x1.921fb6p-7f
+
+static inline draw3_t draw_bits(uint32_t w0, uint32_t w1) {
+    draw3_t d;
+    d.ur = (float)(w0 >> 8) * 0x1p-24f;
+    d.kt = 2u * (w1 >> 24);
+    d.bt = (float)((w1 >> 8) & 0xffffu) * (ORC_TWO_PI_256 * 0x1p-16f);
+    d.kp = w1 & 0xffu;
+    d.bp = (float)(w0 & 0xffu) * (ORC_PI_256 * 0x1p-8f);
+    return d;
+}
+
+static inline draw3_t draw_floats(float ut, float up, float ur) {
+    draw3_t d;
+    d.ur = ur;
+    float tt = ut * 256.0f, kt = floorf(tt);
+    d.kt = 2u * ((uint32_t)(int)kt & 0xffu);
+    d.bt = (tt - kt) * ORC_TWO_PI_256;
+    float tp = up * 256.0f, kp = floorf(tp);
+    d.kp = (uint32_t)(int)kp & 0xffu;
+    d.bp = (tp - kp) * ORC_PI_256;
+    return d;
+}
+
+static inline draw3_t draw_at(uint64_t gid, uint64_t seed, uint32_t step) {
+    uint32_t ctr[2] = {(uint32_t)gid, step}, o[2];
+    orc_philox2x32_10(ctr, orc_fold_key(seed, gid >> 32, 0), o);
+    return draw_bits(o[0], o[1]);
+}
+
+/* the same draws as plain uniforms: u_theta = theta / 2 pi, u_phi = phi / pi (exact in binary32), u_rand */
+static inline void draw3(uint64_t gid, uint64_t seed, uint32_t step, uint32_t stream, float *a, float *b, float *c) {
+    if (stream != 0u) { /* emission sampler: Philox4x32-10, counter (id_lo, id_hi, step, stream), key = seed */
+        uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), step, stream};
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t o[4];
+        orc_philox4x32_10(ctr, key, o);
+        *a = u01(o[0]);
+        *b = u01(o[1]);
+        *c = u01(o[2]);
+        return;
+    }
+    uint32_t ctr[2] = {(uint32_t)gid, step}, o[2];
+    orc_philox2x32_10(ctr, orc_fold_key(seed, gid >> 32, 0), o);
+    *a = (float)(o[1] >> 8) * 0x1p-24f;
+    *b = (float)(((o[1] & 0xffu) << 8) | (o[0] & 0xffu)) * 0x1p-16f;
+    *c = (float)(o[0] >> 8) * 0x1p-24f;
+}
+
+/* fill u_theta,u_phi,u_rand[n] with the draws of photons id_base+i at `step` */
 void orc_philox_uniforms(uint64_t n, uint64_t id_base, uint64_t seed, uint32_t step, uint32_t stream, float *ut,
                          float *up, float *ur) {
 #pragma omp parallel for schedule(static)
@@ -84,55 +157,71 @@ void orc_philox_uniforms(uint64_t n, uint64_t id_base, uint64_t seed, uint32_t s
 /* ------------------------------------------------------------------------------------------ */
 /* binary32 twin                                                                                */
 /* ------------------------------------------------------------------------------------------ */
-/* sin(pi t), cos(pi t), t in [0,2]: exact quadrant reduction + Taylor kernels, fmaf only */
-void orc_sincospi_f32(float t, float *s, float *c) {
-    const float S0 = 0x1.921fb6p+1f, S1 = -0x1.4abbcep+2f, S2 = 0x1.466bc6p+1f, S3 = -0x1.32d2ccp-1f,
-                S4 = 0x1.507834p-4f;
-    const float C1 = -0x1.3bd3ccp+2f, C2 = 0x1.03c1fp+2f, C3 = -0x1.55d3c8p+0f, C4 = 0x1.e1f506p-3f,
-                C5 = -0x1.a6d1f2p-6f;
-    float q = rintf(t + t);
-    float r = fmaf(q, -0.5f, t);
-    int qi = (int)q;
-    float r2 = r * r;
-    float ps = fmaf(r2, S4, S3);
-    ps = fmaf(r2, ps, S2);
-    ps = fmaf(r2, ps, S1);
-    ps = fmaf(r2, ps, S0);
-    float sr = r * ps;
-    float pc = fmaf(r2, C5, C4);
-    pc = fmaf(r2, pc, C3);
-    pc = fmaf(r2, pc, C2);
-    pc = fmaf(r2, pc, C1);
-    float cr = fmaf(r2, pc, 1.0f);
-    float a = (qi & 1) ? cr : sr;
-    float b = (qi & 1) ? sr : cr;
-    *s = (qi & 2) ? -a : a;
-    *c = ((qi + 1) & 2) ? -b : b;
+/* Direction table (sin, cos)(2 pi k / 512), double rounded once to binary32 (same expression as pcl_init). */
+static float g_trig[512][2];
+static int g_trig_ready = 0;
+static void trig_init(void) {
+    if (g_trig_ready) return;
+#pragma omp critical(orc_trig)
+    {
+        if (!g_trig_ready) {
+            for (int k = 0; k < 512; ++k) {
+                const double a = 2.0 * 3.14159265358979323846 * (double)k / 512.0;
+                g_trig[k][0] = (float)sin(a);
+                g_trig[k][1] = (float)cos(a);
+            }
+            g_trig_ready = 1;
+        }
+    }
 }
 
-/* light.py:305-311 in binary32; returns 1 if scattered */
-static inline int scatter_one_f32(float dx, float dy, float dz, float e, float ut, float up, float ur, float k,
-                                  float c, uint32_t mode, float *vx, float *vy, float *vz) {
+/* sin, cos of (table angle k) + b by the addition theorem, cos b = 1 - b^2/2, sin b = b - b^3/6; mul / fmaf only */
+void orc_sincos_tab(uint32_t k, float b, float *s, float *c) {
+    trig_init();
+    const float sa = g_trig[k & 511u][0], ca = g_trig[k & 511u][1];
+    const float b2 = b * b;
+    const float cb = fmaf(b2, -0.5f, 1.0f);
+    const float sb = fmaf(b * b2, -0x1.555556p-3f, b);
+    *s = fmaf(sa, cb, ca * sb);
+    *c = fmaf(ca, cb, -(sa * sb));
+}
+
+/* light.py:305-311 in binary32; returns 1 if scattered.  The reference's test pcoll = k*norm [e^4] >= rand is
+ * evaluated squared, norm^2 [e^8] >= (rand / k)^2 (both sides >= 0; kinv = 1/k folded in double by the caller),
+ * which is the operation sequence of the CUDA kernels (no square root). */
+static inline int scatter_one_f32(float dx, float dy, float dz, float e, const draw3_t *d, float kinv, float c,
+                                  uint32_t mode, float *vx, float *vy, float *vz) {
     float s = dx * dx;
     s = fmaf(dy, dy, s);
     s = fmaf(dz, dz, s);
-    float norm = sqrtf(s);
-    float pcoll = k * norm;
+    float q = d->ur * kinv;
+    float lhs = s;
     if (mode & ORC_WAVELENGTH) {
         float e2 = e * e;
         float e4 = e2 * e2;
-        pcoll = pcoll * e4;
+        lhs = s * (e4 * e4);
     }
-    if (!(pcoll >= ur)) return 0;
+    if (!(lhs >= q * q)) return 0;
     if (mode & ORC_DELETE) return 1;
     float st, ct, sp, cp;
-    orc_sincospi_f32(ut + ut, &st, &ct);
-    orc_sincospi_f32(up, &sp, &cp);
+    orc_sincos_tab(d->kt, d->bt, &st, &ct);
+    orc_sincos_tab(d->kp, d->bp, &sp, &cp);
     float cs = c * st;
     *vx = cs * cp;
     *vy = cs * sp;
     *vz = c * ct;
     return 1;
+}
+
+/* 1/k as the CUDA library folds it (pcl_fill_stepk) */
+static inline float kinv_of(float k) {
+    double kd = (double)k;
+    if (kd > 0.0) {
+        double inv = 1.0 / kd;
+        return inv > 3.4028234663852886e38 ? 3.4028234663852886e38f : (float)inv;
+    }
+    if (kd == 0.0) return 3.4028234663852886e38f;
+    return NAN;
 }
 
 static inline void tally_one_f32(float x, float y, float z, float dx, float dy, float dz, float vx, float vy,
@@ -191,6 +280,8 @@ void orc_photon_step_f32(uint64_t n, float *x, float *y, float *z, float *vx, fl
                          int64_t *row) {
     int64_t acc[ORC_TALLY_COLS];
     memset(acc, 0, sizeof(acc));
+    const float kinv = kinv_of(k);
+    trig_init();
 #pragma omp parallel
     {
         int64_t loc_row[ORC_TALLY_COLS];
@@ -198,21 +289,23 @@ void orc_photon_step_f32(uint64_t n, float *x, float *y, float *z, float *vx, fl
 #pragma omp for schedule(static) nowait
         for (int64_t i = 0; i < (int64_t)n; ++i) {
             float xx = x[i];
-            if (xx != xx) continue;
+            if (xx != xx) { /* retired slot: the kernels step it with dt = 0 (x stays NaN, y and z keep their value) */
+                y[i] = y[i] + vy[i] * 0.f;
+                z[i] = z[i] + vz[i] * 0.f;
+                continue;
+            }
             loc_row[ORC_T_LIVE_IN] += 1;
             float dx = vx[i] * dt, dy = vy[i] * dt, dz = vz[i] * dt;
             xx = xx + dx;
             float yy = y[i] + dy, zz = z[i] + dz;
-            float a, b, r;
+            draw3_t d;
             if (ur) {
-                a = ut ? ut[i] : 0.f;
-                b = up ? up[i] : 0.f;
-                r = ur[i];
+                d = draw_floats(ut ? ut[i] : ur[i], up ? up[i] : ur[i], ur[i]);
             } else {
-                draw3(id_base + (id ? (uint64_t)id[i] : (uint64_t)i), seed, step, 0u, &a, &b, &r);
+                d = draw_at(id_base + (id ? (uint64_t)id[i] : (uint64_t)i), seed, step);
             }
             float nvx = vx[i], nvy = vy[i], nvz = vz[i];
-            int sc = scatter_one_f32(dx, dy, dz, e ? e[i] : 1.f, a, b, r, k, c, mode, &nvx, &nvy, &nvz);
+            int sc = scatter_one_f32(dx, dy, dz, e ? e[i] : 1.f, &d, kinv, c, mode, &nvx, &nvy, &nvz);
             int absorbed = sc && (mode & ORC_DELETE);
             int escaped = 0;
             if (!absorbed && r2_escape > 0.f) {
@@ -251,21 +344,21 @@ void orc_scatter_f32(uint64_t n, float *x, float *vx, float *vy, float *vz, cons
                      float c, uint32_t mode, uint64_t seed, uint32_t step, const float *ut, const float *up,
                      const float *ur, int32_t *flags, int64_t *row) {
     int64_t alive = 0, scat = 0, absd = 0, livein = 0;
+    const float kinv = kinv_of(k);
+    trig_init();
 #pragma omp parallel for schedule(static) reduction(+ : alive, scat, absd, livein)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         int32_t flag = 0;
         if (x[i] == x[i]) {
             livein += 1;
-            float a, b, r;
+            draw3_t d;
             if (ur) {
-                a = ut ? ut[i] : 0.f;
-                b = up ? up[i] : 0.f;
-                r = ur[i];
+                d = draw_floats(ut ? ut[i] : ur[i], up ? up[i] : ur[i], ur[i]);
             } else {
-                draw3(id_base + (id ? (uint64_t)id[i] : (uint64_t)i), seed, step, 0u, &a, &b, &r);
+                d = draw_at(id_base + (id ? (uint64_t)id[i] : (uint64_t)i), seed, step);
             }
             float nvx = 0.f, nvy = 0.f, nvz = 0.f;
-            int sc = scatter_one_f32(dx[i], dy[i], dz[i], e ? e[i] : 1.f, a, b, r, k, c, mode, &nvx, &nvy, &nvz);
+            int sc = scatter_one_f32(dx[i], dy[i], dz[i], e ? e[i] : 1.f, &d, kinv, c, mode, &nvx, &nvy, &nvz);
             if (sc) {
                 flag = 1;
                 scat += 1;

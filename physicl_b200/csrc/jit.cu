@@ -249,13 +249,14 @@ extern "C" int pcl_photon_steps_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kern
     PCL_REQUIRE(ctx, k && k->fn && p && sp && rng && tally_table, "null argument");
     PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
     PCL_REQUIRE(ctx, p->n < (1ull << 32), "a shard holds fewer than 2^32 slots");
+    PCL_REQUIRE(ctx, (p->id_base & 0xffffffffull) + p->n <= (1ull << 32), "the global ids of a shard must not cross a multiple of 2^32");
     if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
     PCL_REQUIRE(ctx, nsteps == 1 || rng->u_rand == nullptr, "multi-step runs draw from Philox; injected uniforms are per step");
     cudaStream_t st = (cudaStream_t)stream;
     PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
     if (p->n == 0) return 0;
     StepK K;
-    int rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
+    int rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes, p->id_base);
     if (rc == 0) rc = fill_varn(ctx, K, vn);
     if (rc) return rc;
     int aligned = pcl_aligned16(p->x) && pcl_aligned16(p->y) && pcl_aligned16(p->z) && pcl_aligned16(p->vx) &&
@@ -284,7 +285,7 @@ extern "C" int pcl_scatter_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kernel *k
     if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
     if (p->n == 0) return 0;
     StepK K;
-    int rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr);
+    int rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr, p->id_base);
     if (rc == 0) rc = fill_varn(ctx, K, vn);
     if (rc) return rc;
     pcl_soa view = *p;

@@ -1,6 +1,7 @@
 // Context management, error reporting and the on-box peak probes of the physicl_b200 C ABI.
 // Stands in for cl.create_some_context()/cl.CommandQueue()/get_device_info()
 // (reference physicl/__init__.py:428-429, :470-499).
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -58,6 +59,21 @@ extern "C" int pcl_init(int device, pcl_ctx **out) {
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     ctx->hbm_bytes = prop.totalGlobalMem;
     snprintf(ctx->name, sizeof(ctx->name), "%.120s", prop.name);
+    {  // direction table of the photon kernels: (sin, cos)(2 pi k / 512) in double, rounded once to binary32
+        float2 host[PCL_TRIG_N];
+        for (int k = 0; k < PCL_TRIG_N; ++k) {
+            const double a = 2.0 * 3.14159265358979323846 * (double)k / (double)PCL_TRIG_N;
+            host[k] = make_float2((float)sin(a), (float)cos(a));
+        }
+        cudaError_t e2 = cudaMalloc(&ctx->trig, sizeof(host));
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->trig, host, sizeof(host), cudaMemcpyHostToDevice);
+        if (e2 != cudaSuccess) {
+            pcl_set_error(nullptr, "pcl_init: direction table: %s", cudaGetErrorString(e2));
+            if (ctx->trig) cudaFree(ctx->trig);
+            free(ctx);
+            return -7;
+        }
+    }
     *out = ctx;
     return 0;
 }
@@ -68,6 +84,7 @@ extern "C" int pcl_destroy(pcl_ctx *ctx) {
     pcl_hostpipe_destroy(ctx);
     if (ctx->scan_buf) cudaFree(ctx->scan_buf);
     if (ctx->grav_part) cudaFree(ctx->grav_part);
+    if (ctx->trig) cudaFree(ctx->trig);
     free(ctx);
     return 0;
 }

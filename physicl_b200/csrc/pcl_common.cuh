@@ -1,8 +1,8 @@
 // Shared device/host helpers for the physicl_b200 kernels (sm_100a only).
 // Arithmetic contract: this library is compiled with -fmad=false, so `a*b+c` is never contracted;
-// every fused multiply-add is an explicit fmaf().  The CPU oracle twin (oracle/c/oracle_f32.c) uses
-// the same sequence of IEEE-754 binary32 operations (mul, add, fma, sqrt, rint), which is what
-// makes the integer tallies bit-exact between the two.
+// every fused multiply-add is an explicit fmaf().  The CPU oracle twin (oracle/c/oracle.c, orc_*_f32) uses
+// the same sequence of IEEE-754 binary32 operations (mul, add, fma, floor, int<->float conversions) and the
+// same direction table, which is what makes the integer tallies bit-exact between the two.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,6 +39,8 @@ struct pcl_ctx {
     float *grav_part;
     size_t grav_cap;
     pcl_hostpipe *pipe;
+    // (sin, cos)(2 pi k / 512): the direction table of the photon kernels (pcl_device.cuh), built at pcl_init
+    float2 *trig;
 };
 
 void pcl_set_error(pcl_ctx *ctx, const char *fmt, ...);
@@ -92,6 +94,6 @@ static inline unsigned pcl_stream_grid(const pcl_ctx *ctx, uint64_t work_items, 
 
 struct StepK;  // pcl_photon_body.cuh; filled by photon.cu for the pre-compiled and the run-time kernels
 int pcl_fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
-                   const pcl_planes *planes);
+                   const pcl_planes *planes, uint64_t id_base);
 
 #endif  // __CUDACC__

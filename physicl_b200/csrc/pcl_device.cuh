@@ -1,6 +1,7 @@
 // Device-only helpers shared by the hand-written kernels and by run-time compiled (NVRTC) kernels:
-// Philox4x32-10, mantissa uniforms and the reproducible sin(pi t)/cos(pi t).  No host code, no
-// standard headers needed under NVRTC.
+// Philox (4x32 for the emission sampler, 2x32 for the photon steps), mantissa uniforms and the
+// reproducible table-driven sin/cos of the scattering angles.  No host code, no standard headers
+// needed under NVRTC.
 #pragma once
 #ifdef __CUDACC_RTC__
 typedef unsigned int uint32_t;
@@ -35,40 +36,81 @@ __device__ __forceinline__ uint4 pcl_philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ float pcl_u01(uint32_t r) { return (float)(r >> 8) * 0x1p-24f; }
 
 // ---------------------------------------------------------------------------------------------
-// sin(pi t), cos(pi t) for t in [0, 2], built only from rintf / fmaf / mul so that the CPU twin
-// reproduces it bit for bit.  Quadrant reduction is exact; the kernels are odd/even Taylor
-// polynomials on |r| <= 1/4 (truncation error < 2.5e-9).
+// Philox2x32-10 (same paper): ONE 32x32 multiply per round, 64 random bits per block -- exactly what a
+// photon needs per timestep (24 bits for the collision test, 24 + 16 for the two angles), at half the
+// instructions of Philox4x32.  counter = (global id, step); the ten round keys key + r*W are formed on
+// the host and arrive as kernel parameters, i.e. as constant-bank operands of the XOR.
 // ---------------------------------------------------------------------------------------------
-#define PCL_S0 0x1.921fb6p+1f    /*  pi           */
-#define PCL_S1 -0x1.4abbcep+2f  /* -pi^3/3!      */
-#define PCL_S2 0x1.466bc6p+1f    /*  pi^5/5!      */
-#define PCL_S3 -0x1.32d2ccp-1f  /* -pi^7/7!      */
-#define PCL_S4 0x1.507834p-4f    /*  pi^9/9!      */
-#define PCL_C1 -0x1.3bd3ccp+2f  /* -pi^2/2!      */
-#define PCL_C2 0x1.03c1fp+2f     /*  pi^4/4!      */
-#define PCL_C3 -0x1.55d3c8p+0f  /* -pi^6/6!      */
-#define PCL_C4 0x1.e1f506p-3f    /*  pi^8/8!      */
-#define PCL_C5 -0x1.a6d1f2p-6f  /* -pi^10/10!    */
+#define PCL_PHILOX2_M 0xD256D193u
+#define PCL_PHILOX2_W 0x9E3779B9u
 
-__device__ __forceinline__ void pcl_sincospi(float t, float &s, float &c) {
-    float q = rintf(t + t);
-    float r = fmaf(q, -0.5f, t);
-    int qi = (int)q;
-    float r2 = r * r;
-    float ps = fmaf(r2, PCL_S4, PCL_S3);
-    ps = fmaf(r2, ps, PCL_S2);
-    ps = fmaf(r2, ps, PCL_S1);
-    ps = fmaf(r2, ps, PCL_S0);
-    float sr = r * ps;
-    float pc = fmaf(r2, PCL_C5, PCL_C4);
-    pc = fmaf(r2, pc, PCL_C3);
-    pc = fmaf(r2, pc, PCL_C2);
-    pc = fmaf(r2, pc, PCL_C1);
-    float cr = fmaf(r2, pc, 1.0f);
-    float a = (qi & 1) ? cr : sr;
-    float b = (qi & 1) ? sr : cr;
-    s = (qi & 2) ? -a : a;
-    c = ((qi + 1) & 2) ? -b : b;
+__device__ __forceinline__ uint2 pcl_philox2x32_10(uint32_t c0, uint32_t c1, const uint32_t (&rk)[10]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi = __umulhi(PCL_PHILOX2_M, c0), lo = PCL_PHILOX2_M * c0;
+        c0 = hi ^ rk[r] ^ c1;
+        c1 = lo;
+    }
+    return make_uint2(c0, c1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sin / cos of the scattering angles, reproducible bit for bit on a CPU: a 512-entry table of
+// (sin, cos)(2 pi k / 512), rounded from double, and the angle addition theorem for the remainder
+//   sin(a + b) = sin a cos b + cos a sin b,   cos(a + b) = cos a cos b - sin a sin b,   0 <= b < 2 pi / 256
+// with cos b = 1 - b^2/2 and sin b = b - b^3/6 (truncation < 1.6e-8 and < 8e-11; the table entries carry the
+// usual 6e-8 rounding).  mul / fmaf only, no quadrant logic, no conversions on the slow pipe.
+// The table sits in shared memory (4 KB per CTA); `at` is the BYTE offset of the entry.
+// ---------------------------------------------------------------------------------------------
+#define PCL_TRIG_N 512
+#define PCL_TRIG_BYTES (PCL_TRIG_N * 8)
+#define PCL_TWO_PI_256 0x1.921fb6p-6f /* 2 pi / 256 : theta = (k8 + f) * this  */
+#define PCL_PI_256 0x1.921fb6p-7f     /* pi / 256   : phi   = (k8 + f) * this  */
+
+__device__ __forceinline__ void pcl_sincos_tab(const unsigned char *tab, uint32_t at, float b, float &s, float &c) {
+    const float2 t = *reinterpret_cast<const float2 *>(tab + at);
+    const float b2 = b * b;
+    const float cb = fmaf(b2, -0.5f, 1.0f);
+    const float sb = fmaf(b * b2, -0x1.555556p-3f, b);
+    s = fmaf(t.x, cb, t.y * sb);
+    c = fmaf(t.y, cb, -(t.x * sb));
+}
+
+// One photon's random numbers for one timestep, in the form the step body consumes them.
+struct pcl_draw3 {
+    float ur;         // U[0,1) of the collision test (24 bits)
+    uint32_t at, ap;  // byte offsets of the table entries below theta and below phi
+    float bt, bp;     // remainders: theta = entry angle + bt (bt < 2 pi/256), phi = entry angle + bp (bp < pi/256)
+};
+
+// from one Philox2x32 block (w0, w1):  ur = w0[31:8];  theta = 2 pi * w1[31:8] / 2^24;  phi = pi * (w1[7:0] : w0[7:0]) / 2^16
+__device__ __forceinline__ pcl_draw3 pcl_draw_bits(uint32_t w0, uint32_t w1) {
+    pcl_draw3 d;
+    d.ur = (float)(w0 >> 8) * 0x1p-24f;
+    d.at = (w1 >> 20) & 0xff0u;                                    // k8 = w1[31:24], entry 2*k8, 8 bytes each
+    d.bt = (float)((w1 >> 8) & 0xffffu) * (PCL_TWO_PI_256 * 0x1p-16f);
+    d.ap = (w1 & 0xffu) << 3;                                      // k8 = w1[7:0], entry k8
+    d.bp = (float)(w0 & 0xffu) * (PCL_PI_256 * 0x1p-8f);
+    return d;
+}
+
+// from injected uniforms (the reference's host draws rtheta = 2 pi u, rphi = pi u, rand; light.py:285)
+__device__ __forceinline__ pcl_draw3 pcl_draw_floats(float ut, float up, float ur) {
+    pcl_draw3 d;
+    d.ur = ur;
+    const float tt = ut * 256.0f, kt = floorf(tt);
+    d.at = ((uint32_t)(int)kt & 0xffu) << 4;
+    d.bt = (tt - kt) * PCL_TWO_PI_256;
+    const float tp = up * 256.0f, kp = floorf(tp);
+    d.ap = ((uint32_t)(int)kp & 0xffu) << 3;
+    d.bp = (tp - kp) * PCL_PI_256;
+    return d;
+}
+
+// copy the table (global, built once per context) into this CTA's shared memory; ends with a CTA barrier
+__device__ __forceinline__ void pcl_trig_to_shared(unsigned char *s_tab, const float2 *g_tab) {
+    for (uint32_t q = threadIdx.x; q < PCL_TRIG_N; q += blockDim.x) reinterpret_cast<float2 *>(s_tab)[q] = g_tab[q];
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------

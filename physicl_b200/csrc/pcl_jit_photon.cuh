@@ -26,16 +26,20 @@
 template <bool INJ>
 __device__ __forceinline__ void pcl_jit_step(const pcl_soa &p, const StepK &K, int64_t *row, int aligned) {
     constexpr bool WAVE = PCL_JIT_WAVE != 0, DEL = PCL_JIT_DEL != 0;
-    uint32_t cnt[C_N];
-#pragma unroll
-    for (int q = 0; q < C_N; ++q) cnt[q] = 0u;
+    __shared__ __align__(16) unsigned char s_tab[PCL_TRIG_BYTES];
+    __shared__ unsigned int s_acc[C_N];
+    if (threadIdx.x < C_N) s_acc[threadIdx.x] = 0u;
+    pcl_trig_to_shared(s_tab, K.trig);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (aligned) {
         const uint64_t nvec = pcl_valid_slots(p) / 4;
         const bool has_e = p.e != nullptr, has_id = p.id != nullptr;
-        for (uint64_t g = t0; g < nvec; g += stride) {
-            const uint64_t i = g * 4;
+        const uint64_t lane = threadIdx.x & 31u;
+        // whole warps enter the loop body together (warp-level tally hand-over)
+        for (uint64_t g0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); g0 < nvec; g0 += stride) {
+            const uint64_t g = g0 + lane;
+            const bool in = g < nvec;
+            const uint64_t i = (in ? g : g0) * 4;
             float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
             float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
             float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -50,14 +54,17 @@ __device__ __forceinline__ void pcl_jit_step(const pcl_soa &p, const StepK &K, i
             }
             uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
             if (p.nscat) nsc = pcl_ld4u(p.nscat + i);
-            pcl_step_group4<WAVE, DEL, INJ, true>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, ut4, up4, ur4, cnt);
+            if (!in) x.x = x.y = x.z = x.w = __int_as_float(0x7fc00000);
+            pcl_step_group4_masked<WAVE, DEL, INJ, true, true>(p, K, s_tab, i, x, y, z, vx, vy, vz, e, id, nsc, ut4, up4, ur4, s_acc, in);
         }
-        pcl_step_tail<WAVE, DEL, INJ, true>(p, K, nvec * 4, cnt);
+        pcl_step_tail<WAVE, DEL, INJ, true, true>(p, K, s_tab, nvec * 4, s_acc);
     } else {
         const uint64_t end = pcl_valid_slots(p);
-        for (uint64_t i = t0; i < end; i += stride) pcl_step_scalar<WAVE, DEL, INJ, true>(p, K, i, cnt);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride)
+            pcl_step_scalar<WAVE, DEL, INJ, true, true>(p, K, s_tab, i, s_acc);
     }
-    pcl_flush_tally(cnt, row, K.nplanes);
+    __syncthreads();
+    pcl_row_to_global(s_acc, row);
 }
 
 extern "C" __global__ void __launch_bounds__(256) pcl_jit_photon_step(pcl_soa p, StepK K, int64_t *row, int aligned) {
@@ -74,6 +81,8 @@ template <bool INJ>
 __device__ __forceinline__ void pcl_jit_scatter_body(const pcl_soa &p, const StepK &K, int32_t *flags, int64_t *row,
                                                      uint64_t n) {
     constexpr bool WAVE = PCL_JIT_WAVE != 0, DEL = PCL_JIT_DEL != 0;
+    __shared__ __align__(16) unsigned char s_tab[PCL_TRIG_BYTES];
+    pcl_trig_to_shared(s_tab, K.trig);
     uint32_t cnt[C_PLANE0];
 #pragma unroll
     for (int q = 0; q < C_PLANE0; ++q) cnt[q] = 0u;
@@ -84,22 +93,15 @@ __device__ __forceinline__ void pcl_jit_scatter_body(const pcl_soa &p, const Ste
         int32_t flag = 0;
         if (xx == xx) {
             cnt[C_LIVEIN] += 1u;
-            float ut, up, ur;
-            if (INJ) {
-                ut = K.u_theta[i];
-                up = K.u_phi[i];
-                ur = K.u_rand[i];
-            } else {
-                uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-                pcl_draw(K, gid, ut, up, ur);
-            }
+            const pcl_draw3 d = INJ ? pcl_draw_floats(K.u_theta[i], K.u_phi[i], K.u_rand[i])
+                                    : pcl_draw_at(K, K.step, (uint32_t)p.id_base + (p.id ? p.id[i] : (uint32_t)i));
             float vx = 0.f, vy = 0.f, vz = 0.f;
             const float e = p.e ? p.e[i] : 1.f;
             const float dx = p.dx[i], dy = p.dy[i], dz = p.dz[i];
             const double kn = K.kd * pcl_user_n((double)xx, (double)p.y[i], (double)p.z[i], (double)e * K.e0, (double)dx,
                                                 (double)dy, (double)dz, (double)pcl_norm3(dx, dy, dz), K.a_slot, K.n_slot);
-            uint32_t f = pcl_scatter_one<WAVE, DEL, true>(true, dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz, kn);
-            if (f & F_SCATTERED) {
+            const bool hit = pcl_scatter_one<WAVE, DEL, true>(true, dx, dy, dz, e, d, K, s_tab, vx, vy, vz, kn);
+            if (hit) {
                 flag = 1;
                 cnt[C_SCAT] += 1u;
                 if (DEL) {
@@ -112,7 +114,7 @@ __device__ __forceinline__ void pcl_jit_scatter_body(const pcl_soa &p, const Ste
                     if (p.nscat) p.nscat[i] += 1u;
                 }
             }
-            if (!(f & F_ABSORBED)) cnt[C_ALIVE] += 1u;
+            if (!(DEL && hit)) cnt[C_ALIVE] += 1u;
         }
         if (flags) flags[i] = flag;
     }

@@ -5,15 +5,17 @@
 
 struct StepK {
     float dt;
-    float k;
+    float k;          // A*n [* (E0/(h c))^4]: run-time compiled variable-density kernels and diagnostics
+    float kinv;       // 1/k, folded in float64 on the host: the collision test is |dr|^2 [e^8] >= (rand/k)^2
     float c;
-    float r2_escape;  // <= 0: no sphere
-    uint32_t seed_lo, seed_hi;
+    float r2_escape;  // NaN: no sphere (r2 >= NaN is false)
+    uint32_t rk[10];  // Philox2x32 round keys key + r*W (key = fold of seed, high id word, stream)
     uint32_t step;
     uint32_t nplanes;
     uint32_t axis[PCL_MAX_PLANES];
     float loc[PCL_MAX_PLANES];
     const float *u_theta, *u_phi, *u_rand;
+    const float2 *trig;  // (sin, cos)(2 pi k / 512), k < 512, device memory owned by the context
     // run-time compiled variable-density kernels only (light.py:295-299), all float64 like the reference:
     double kd;      // the kernel's scalar `A` [* (E0/(h c))^4 with the wavelength law]
     double e0;      // E = e * e0 for user expressions that read E[gid]
@@ -43,8 +45,17 @@ __device__ __forceinline__ double pcl_user_n(double r0_, double r1_, double r2_,
 
 enum { F_SCATTERED = 1, F_ABSORBED = 2, F_ESCAPED = 4 };
 
-// tally columns held in registers per thread
+// tally columns held in registers per thread (stand-alone kernels: one 32-bit counter per column)
 enum { C_ALIVE, C_XP, C_YP, C_ZP, C_SCAT, C_ABS, C_ESC, C_LIVEIN, C_PLANE0, C_N = C_PLANE0 + PCL_MAX_PLANES };
+
+// The fused kernels count in PACKED form: four 8-bit fields per word, in column order
+//   a = ALIVE | XP << 8 | YP << 16 | ZP << 24      b = SCAT | ABS << 8 | ESC << 16 | LIVEIN << 24
+//   p0 = planes 0..3                                p1 = planes 4..7
+// A thread owns four photons and hands its words to pcl_tally_to_shared after every timestep, so a field never
+// exceeds 4 per thread and 128 per warp: one warp reduction per word, no carries between fields.
+struct pcl_tally4 {
+    uint32_t a, b, p0, p1;
+};
 
 __device__ __forceinline__ float pcl_norm3(float dx, float dy, float dz) {
     float s = dx * dx;
@@ -54,55 +65,58 @@ __device__ __forceinline__ float pcl_norm3(float dx, float dy, float dz) {
 }
 
 // The scatter decision and the new direction for one photon.  dx,dy,dz is this step's dr.
+//   reference (light.py:305-307):  norm = sqrt(d0^2+d1^2+d2^2);  pcoll = A n norm [ (hc/E)^-4 ];  pcoll >= rand
+//   here, same inequality squared (both sides are >= 0):  d0^2+d1^2+d2^2 [ e^8 ] >= (rand / k)^2
+// which needs no square root (the IEEE sqrtf and its slow-path branches were ~25 instructions per photon).
+// 1/k comes from the host (float64 fold): k = 0 -> FLT_MAX (only rand = 0 scatters), k < 0 -> NaN (never).
 // Written without branches on purpose: every lane evaluates both angles and selects, so the compiler
 // can interleave the four photons a thread owns (independent chains) instead of serialising four
 // divergent bodies.  At warp level nothing is lost: with pcoll ~ 0.3 some lane scatters in
 // practically every warp, so the divergent form executed both sides anyway.
 // VARN: the collision probability is formed in float64 from kn = kd * n(r) (see pcl_user_n).
 template <bool WAVE, bool DEL, bool VARN = false>
-__device__ __forceinline__ uint32_t pcl_scatter_one(bool live, float dx, float dy, float dz, float e,
-                                                    float ut, float up, float ur, float k, float c,
-                                                    float &vx, float &vy, float &vz, double kn = 0.0) {
-    float norm = pcl_norm3(dx, dy, dz);
+__device__ __forceinline__ bool pcl_scatter_one(bool live, float dx, float dy, float dz, float e, const pcl_draw3 &d,
+                                                const StepK &K, const unsigned char *tab, float &vx, float &vy,
+                                                float &vz, double kn = 0.0) {
+    float s = dx * dx;
+    s = fmaf(dy, dy, s);
+    s = fmaf(dz, dz, s);
     bool hit;
     if (VARN) {
-        double pd = kn * (double)norm;
+        double pd = kn * (double)sqrtf(s);
         if (WAVE) {
             double e2 = (double)e * (double)e;
             pd = pd * (e2 * e2);
         }
-        hit = live && (pd >= (double)ur);
+        hit = live && (pd >= (double)d.ur);
     } else {
-        float pcoll = k * norm;
+        const float q = d.ur * K.kinv;
+        float lhs = s;
         if (WAVE) {
-            float e2 = e * e;
-            float e4 = e2 * e2;
-            pcoll = pcoll * e4;
+            const float e2 = e * e;
+            const float e4 = e2 * e2;
+            lhs = s * (e4 * e4);
         }
-        hit = live && (pcoll >= ur);
+        hit = live && (lhs >= q * q);
     }
-    if (DEL) return hit ? (F_SCATTERED | F_ABSORBED) : 0u;
+    if (DEL) return hit;
     float st, ct, sp, cp;
-    pcl_sincospi(ut + ut, st, ct);  // theta = 2*pi*u
-    pcl_sincospi(up, sp, cp);       // phi   =   pi*u
-    float cs = c * st;
+    pcl_sincos_tab(tab, d.at, d.bt, st, ct);  // theta = 2 pi u
+    pcl_sincos_tab(tab, d.ap, d.bp, sp, cp);  // phi   =   pi u
+    const float cs = K.c * st;
     vx = hit ? cs * cp : vx;
     vy = hit ? cs * sp : vy;
-    vz = hit ? c * ct : vz;
-    return hit ? F_SCATTERED : 0u;
+    vz = hit ? K.c * ct : vz;
+    return hit;
 }
 
-__device__ __forceinline__ void pcl_draw_at(const StepK &K, uint32_t step, uint64_t gid, float &ut, float &up, float &ur) {
-    uint4 r = pcl_philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), step, 0u),
-                                make_uint2(K.seed_lo, K.seed_hi));
-    ut = pcl_u01(r.x);
-    up = pcl_u01(r.y);
-    ur = pcl_u01(r.z);
-}
-__device__ __forceinline__ void pcl_draw(const StepK &K, uint64_t gid, float &ut, float &up, float &ur) {
-    pcl_draw_at(K, K.step, gid, ut, up, ur);
+// this photon's draws for timestep `step`: Philox2x32-10 on (low word of the global id, step)
+__device__ __forceinline__ pcl_draw3 pcl_draw_at(const StepK &K, uint32_t step, uint32_t gid_lo) {
+    const uint2 w = pcl_philox2x32_10(gid_lo, step, K.rk);
+    return pcl_draw_bits(w.x, w.y);
 }
 
+// stand-alone tallies (ScatterSignMeasureStep / ScatterMeasureStep kernels): one counter per column
 template <int NC>
 __device__ __forceinline__ void pcl_tally_one(const StepK &K, bool on, float x, float y, float z, float dx,
                                               float dy, float dz, float vx, float vy, float vz,
@@ -150,37 +164,101 @@ static_assert((int)C_ALIVE == (int)PCL_T_ALIVE && (int)C_XP == (int)PCL_T_XP && 
                   (int)C_PLANE0 == (int)PCL_T_PLANE0 && (int)C_N == (int)PCL_TALLY_COLS,
               "register tally layout must match the ABI row layout");
 
+// Per-timestep tally hand-over of a WARP (all 32 lanes must call it).  Four counters travel as the 8-bit
+// fields of one word through ONE warp reduction, and lane q then adds column q to the CTA's row with a single
+// predicated shared-memory atomic.  acc: unsigned int[PCL_TALLY_COLS] in shared memory.
+template <bool PL>
+__device__ __forceinline__ void pcl_tally_to_shared(const pcl_tally4 &t, unsigned int *acc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t sh = 8u * (lane & 3u);
+    uint32_t mine = 0u;
+    uint32_t w = __reduce_add_sync(0xffffffffu, t.a);
+    if ((lane >> 2) == 0u) mine = w >> sh;
+    w = __reduce_add_sync(0xffffffffu, t.b);
+    if ((lane >> 2) == 1u) mine = w >> sh;
+    if (PL) {
+        w = __reduce_add_sync(0xffffffffu, t.p0);
+        if ((lane >> 2) == 2u) mine = w >> sh;
+        w = __reduce_add_sync(0xffffffffu, t.p1);
+        if ((lane >> 2) == 3u) mine = w >> sh;
+    }
+    mine &= 0xffu;
+    if (lane < (PL ? 16u : 8u) && mine) atomicAdd(&acc[lane], mine);
+}
+
+// the same for code that only part of a warp executes (tails, scalar kernels): plain shared atomics
+__device__ __forceinline__ void pcl_tally_to_shared_divergent(const pcl_tally4 &t, unsigned int *acc) {
+    const uint32_t w[4] = {t.a, t.b, t.p0, t.p1};
+#pragma unroll
+    for (int q = 0; q < C_N; ++q) {
+        const uint32_t v = (w[q >> 2] >> (8 * (q & 3))) & 0xffu;
+        if (v) atomicAdd(&acc[q], v);
+    }
+}
+
+// CTA row in shared memory -> tally row in HBM (call after a CTA barrier)
+__device__ __forceinline__ void pcl_row_to_global(const unsigned int *acc, int64_t *row) {
+    if (threadIdx.x < C_N) {
+        const unsigned int v = acc[threadIdx.x];
+        if (v) atomicAdd((unsigned long long *)&row[threadIdx.x], (unsigned long long)v);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One photon, one timestep: kinematics -> scatter -> escape -> tallies.  Shared by every fused kernel.
-// On return x is NaN if the photon retired; v holds the new direction if it scattered.
+// On return x is NaN if the photon retired; v holds the new direction if it scattered (return value).
+// A retired slot (x = NaN) is stepped with dt = 0: it stays retired, its other planes keep their bits.
 // ---------------------------------------------------------------------------------------------
-template <bool WAVE, bool DEL, bool VARN = false, int NC>
-__device__ __forceinline__ uint32_t pcl_photon_one(const StepK &K, float &x, float &y, float &z, float &vx, float &vy,
-                                                   float &vz, float e, float ut, float up, float ur,
-                                                   uint32_t (&cnt)[NC]) {
-    const bool live = x == x;  // a retired slot stays retired: NaN + dx is NaN
-    cnt[C_LIVEIN] += live ? 1u : 0u;
-    float dx = vx * K.dt, dy = vy * K.dt, dz = vz * K.dt;
-    float xx = x + dx, yy = y + dy, zz = z + dz;
+template <bool WAVE, bool DEL, bool VARN, bool PL>
+__device__ __forceinline__ bool pcl_photon_one(const StepK &K, const unsigned char *tab, float &x, float &y, float &z,
+                                               float &vx, float &vy, float &vz, float e, const pcl_draw3 &d,
+                                               pcl_tally4 &t) {
+    const bool live = x == x;
+    const float dte = live ? K.dt : 0.f;
+    const float dx = vx * dte, dy = vy * dte, dz = vz * dte;
+    const float xx = x + dx, yy = y + dy, zz = z + dz;  // NaN + dx is NaN
     double kn = 0.0;
     if (VARN)  // n(r) at the position reached in this timestep: the reference scatters after r += dr
         kn = K.kd * pcl_user_n((double)xx, (double)yy, (double)zz, (double)e * K.e0, (double)dx, (double)dy, (double)dz,
                                (double)pcl_norm3(dx, dy, dz), K.a_slot, K.n_slot);
-    uint32_t f = pcl_scatter_one<WAVE, DEL, VARN>(live, dx, dy, dz, e, ut, up, ur, K.k, K.c, vx, vy, vz, kn);
+    const bool hit = pcl_scatter_one<WAVE, DEL, VARN>(live, dx, dy, dz, e, d, K, tab, vx, vy, vz, kn);
     float r2 = xx * xx;
     r2 = fmaf(yy, yy, r2);
     r2 = fmaf(zz, zz, r2);
-    const bool esc = live && !(f & F_ABSORBED) && K.r2_escape > 0.f && r2 >= K.r2_escape;
-    f |= esc ? F_ESCAPED : 0u;
-    cnt[C_SCAT] += (f & F_SCATTERED) ? 1u : 0u;
-    cnt[C_ABS] += (f & F_ABSORBED) ? 1u : 0u;
-    cnt[C_ESC] += esc ? 1u : 0u;
-    const bool gone = (f & (F_ABSORBED | F_ESCAPED)) != 0u;
-    pcl_tally_one(K, live && !gone, xx, yy, zz, dx, dy, dz, vx, vy, vz, cnt);
-    x = (live && !gone) ? xx : __int_as_float(0x7fc00000);  // retired slots hold the canonical quiet NaN
-    y = live ? yy : y;  // slots retired earlier keep their last position
-    z = live ? zz : z;
-    return f;
+    const bool absorbed = DEL && hit;
+    const bool esc = (r2 >= K.r2_escape) && !absorbed;  // false for retired slots (r2 is NaN) and without a sphere
+    const bool gone = absorbed || esc;
+    const bool on = live && !gone;
+    t.b += hit ? 1u : 0u;
+    if (DEL) t.b += hit ? (1u << 8) : 0u;
+    t.b += esc ? (1u << 16) : 0u;
+    t.b += live ? (1u << 24) : 0u;
+    uint32_t m = 1u;
+    m += (vx > 0.f) ? (1u << 8) : 0u;
+    m += (vy > 0.f) ? (1u << 16) : 0u;
+    m += (vz > 0.f) ? (1u << 24) : 0u;
+    t.a += on ? m : 0u;
+    if (PL) {
+#pragma unroll
+        for (int q = 0; q < PCL_MAX_PLANES; ++q) {
+            if ((uint32_t)q < K.nplanes) {
+                const uint32_t ax = K.axis[q];
+                const float r = ax == 0 ? xx : (ax == 1 ? yy : zz);
+                const float dd = ax == 0 ? dx : (ax == 1 ? dy : dz);
+                const float prev = r - dd;  // light.py:386: obj.r[0] - obj.dr[0], evaluated after r += dr
+                const float loc = K.loc[q];
+                const bool cross = on && ((prev <= loc && loc <= r) || (prev >= loc && loc >= r));
+                if (q < 4)
+                    t.p0 += cross ? (1u << (8 * q)) : 0u;
+                else
+                    t.p1 += cross ? (1u << (8 * (q - 4))) : 0u;
+            }
+        }
+    }
+    x = on ? xx : __int_as_float(0x7fc00000);  // retired slots hold the quiet NaN 0x7fc00000 (NaN + 0 would be 0x7fffffff)
+    y = yy;
+    z = zz;
+    return hit;
 }
 
 // number of valid slots: the view's n, or the device-resident count when the caller keeps it there
@@ -194,31 +272,30 @@ __device__ __forceinline__ uint64_t pcl_valid_slots(const pcl_soa &p) {
 
 // Four consecutive photons held in registers: step them and write back in place (r always, v and
 // nscat only when one of the four scattered).  Shared by the register-load and the TMA-staged kernels.
-template <bool WAVE, bool DEL, bool INJ, bool VARN = false, int NC>
-__device__ __forceinline__ void pcl_step_group4(const pcl_soa &p, const StepK &K, uint64_t i, float4 x, float4 y, float4 z,
-                                                float4 vx, float4 vy, float4 vz, float4 e, uint4 id, bool has_id, uint4 nsc,
-                                                float4 ut4, float4 up4, float4 ur4, uint32_t (&cnt)[NC]) {
-    uint32_t any_scat = 0u;
-    float ut[4], up[4], ur[4];
+// All 32 lanes of a warp must call it together (warp-level tally hand-over); a lane without a group of its own
+// passes x = NaN (counts nothing) and store = false.  acc: the CTA's shared row.
+template <bool WAVE, bool DEL, bool INJ, bool VARN, bool PL>
+__device__ __forceinline__ void pcl_step_group4_masked(const pcl_soa &p, const StepK &K, const unsigned char *tab, uint64_t i,
+                                                       float4 x, float4 y, float4 z, float4 vx, float4 vy, float4 vz, float4 e,
+                                                       uint4 id, uint4 nsc, float4 ut4, float4 up4, float4 ur4,
+                                                       unsigned int *acc, bool store) {
+    bool any_scat = false;
+    pcl_draw3 d[4];
+    const uint32_t base_lo = (uint32_t)p.id_base;
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {  // four independent Philox chains: the compiler interleaves them
-        if (INJ) {
-            ut[l] = pcl_f4(ut4, l);
-            up[l] = pcl_f4(up4, l);
-            ur[l] = pcl_f4(ur4, l);
-        } else {
-            uint64_t gid = p.id_base + (has_id ? (uint64_t)pcl_u4(id, l) : (i + (uint64_t)l));
-            pcl_draw(K, gid, ut[l], up[l], ur[l]);
-        }
-    }
+    for (int l = 0; l < 4; ++l)  // four independent Philox chains: the compiler interleaves them
+        d[l] = INJ ? pcl_draw_floats(pcl_f4(ut4, l), pcl_f4(up4, l), pcl_f4(ur4, l)) : pcl_draw_at(K, K.step, base_lo + pcl_u4(id, l));
+    pcl_tally4 t = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        uint32_t f = pcl_photon_one<WAVE, DEL, VARN>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                     pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut[l], up[l], ur[l], cnt);
-        const bool sc = !DEL && (f & F_SCATTERED);
-        any_scat |= sc ? 1u : 0u;
+        const bool hit = pcl_photon_one<WAVE, DEL, VARN, PL>(K, tab, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                             pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), d[l], t);
+        const bool sc = !DEL && hit;
+        any_scat = any_scat || sc;
         pcl_u4(nsc, l) += sc ? 1u : 0u;
     }
+    pcl_tally_to_shared<PL>(t, acc);
+    if (!store) return;
     pcl_st4(p.x + i, x);
     pcl_st4(p.y + i, y);
     pcl_st4(p.z + i, z);
@@ -230,27 +307,22 @@ __device__ __forceinline__ void pcl_step_group4(const pcl_soa &p, const StepK &K
     }
 }
 
-// one slot, scalar accesses
-template <bool WAVE, bool DEL, bool INJ, bool VARN = false, int NC>
-__device__ __forceinline__ void pcl_step_scalar(const pcl_soa &p, const StepK &K, uint64_t i, uint32_t (&cnt)[NC]) {
-    float x = p.x[i];
-    if (x != x) return;
+// one slot, scalar accesses; callable from divergent code
+template <bool WAVE, bool DEL, bool INJ, bool VARN, bool PL>
+__device__ __forceinline__ void pcl_step_scalar(const pcl_soa &p, const StepK &K, const unsigned char *tab, uint64_t i,
+                                                unsigned int *acc) {
+    float x = p.x[i];  // a retired slot goes through the same arithmetic as in the vector path (dt = 0)
     float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
-    float ut, up, ur;
-    if (INJ) {
-        ut = K.u_theta[i];
-        up = K.u_phi[i];
-        ur = K.u_rand[i];
-    } else {
-        uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-        pcl_draw(K, gid, ut, up, ur);
-    }
+    const pcl_draw3 d = INJ ? pcl_draw_floats(K.u_theta[i], K.u_phi[i], K.u_rand[i])
+                            : pcl_draw_at(K, K.step, (uint32_t)p.id_base + (p.id ? p.id[i] : (uint32_t)i));
     const float e = (WAVE || (VARN && p.e)) ? p.e[i] : 1.f;
-    uint32_t f = pcl_photon_one<WAVE, DEL, VARN>(K, x, y, z, vx, vy, vz, e, ut, up, ur, cnt);
+    pcl_tally4 t = {0u, 0u, 0u, 0u};
+    const bool hit = pcl_photon_one<WAVE, DEL, VARN, PL>(K, tab, x, y, z, vx, vy, vz, e, d, t);
+    pcl_tally_to_shared_divergent(t, acc);
     p.x[i] = x;
     p.y[i] = y;
     p.z[i] = z;
-    if (!DEL && (f & F_SCATTERED)) {
+    if (!DEL && hit) {
         p.vx[i] = vx;
         p.vy[i] = vy;
         p.vz[i] = vz;
@@ -259,10 +331,11 @@ __device__ __forceinline__ void pcl_step_scalar(const pcl_soa &p, const StepK &K
 }
 
 // the (< 4 slot) tail after the last full group, scalar, by the first lanes of block 0
-template <bool WAVE, bool DEL, bool INJ, bool VARN = false, int NC>
-__device__ __forceinline__ void pcl_step_tail(const pcl_soa &p, const StepK &K, uint64_t first, uint32_t (&cnt)[NC]) {
+template <bool WAVE, bool DEL, bool INJ, bool VARN, bool PL>
+__device__ __forceinline__ void pcl_step_tail(const pcl_soa &p, const StepK &K, const unsigned char *tab, uint64_t first,
+                                              unsigned int *acc) {
     const uint64_t end = pcl_valid_slots(p);
     const uint64_t i = first + threadIdx.x;
     if (blockIdx.x != 0 || i >= end) return;
-    pcl_step_scalar<WAVE, DEL, INJ, VARN>(p, K, i, cnt);
+    pcl_step_scalar<WAVE, DEL, INJ, VARN, PL>(p, K, tab, i, acc);
 }

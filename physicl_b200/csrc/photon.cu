@@ -29,20 +29,25 @@
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
 pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
-    constexpr int NC = PL ? C_N : C_PLANE0;
-    uint32_t cnt[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    __shared__ __align__(16) unsigned char s_tab[DEL ? 16 : PCL_TRIG_BYTES];
+    __shared__ unsigned int s_acc[C_N];
+    if (threadIdx.x < C_N) s_acc[threadIdx.x] = 0u;
+    if (!DEL) pcl_trig_to_shared(s_tab, K.trig);
+    else __syncthreads();
     const uint64_t nvec = pcl_valid_slots(p) / 4;
     const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
-    for (uint64_t g = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; g < nvec; g += stride) {
-        const uint64_t i = g * 4;
+    const bool has_id = p.id != nullptr;
+    // whole warps enter the loop body together (warp-level tally hand-over): iterate on the warp's first group
+    const uint64_t lane = threadIdx.x & 31u;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * PCL_BLOCK + (threadIdx.x & ~31u); g0 < nvec; g0 += stride) {
+        const uint64_t g = g0 + lane;
+        const bool in = g < nvec;
+        const uint64_t i = (in ? g : g0) * 4;  // lanes past the end redo the warp's first group without storing
         float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
         float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
         float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
         if (WAVE) e = pcl_ld4(p.e + i);
         uint4 id = make_uint4((uint32_t)i, (uint32_t)i + 1u, (uint32_t)i + 2u, (uint32_t)i + 3u);
-        const bool has_id = p.id != nullptr;
         if (has_id) id = pcl_ld4u(p.id + i);
         float4 ut4 = make_float4(0.f, 0.f, 0.f, 0.f), up4 = ut4, ur4 = ut4;
         if (INJ) {
@@ -52,10 +57,12 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
         }
         uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
         if (p.nscat) nsc = pcl_ld4u(p.nscat + i);
-        pcl_step_group4<WAVE, DEL, INJ>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, ut4, up4, ur4, cnt);
+        if (!in) x.x = x.y = x.z = x.w = __int_as_float(0x7fc00000);  // counts nothing
+        pcl_step_group4_masked<WAVE, DEL, INJ, false, PL>(p, K, s_tab, i, x, y, z, vx, vy, vz, e, id, nsc, ut4, up4, ur4, s_acc, in);
     }
-    pcl_step_tail<WAVE, DEL, INJ>(p, K, nvec * 4, cnt);
-    pcl_flush_tally(cnt, row, K.nplanes);
+    pcl_step_tail<WAVE, DEL, INJ, false, PL>(p, K, s_tab, nvec * 4, s_acc);
+    __syncthreads();
+    pcl_row_to_global(s_acc, row);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -102,12 +109,13 @@ __device__ __forceinline__ void pcl_mbar_wait(uint64_t *b, uint32_t parity) {
 template <bool WAVE, bool DEL, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK, PCL_PHOTON_MINB)
 pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
-    constexpr int NC = PL ? C_N : C_PLANE0;
     extern __shared__ __align__(128) unsigned char s_stage_raw[];
     __shared__ __align__(8) uint64_t s_bar[PCL_WARPS][2];
-    uint32_t cnt[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    __shared__ __align__(16) unsigned char s_tab[DEL ? 16 : PCL_TRIG_BYTES];
+    __shared__ unsigned int s_acc[C_N];
+    if (threadIdx.x < C_N) s_acc[threadIdx.x] = 0u;
+    if (!DEL) pcl_trig_to_shared(s_tab, K.trig);
+    else __syncthreads();
     const bool has_id = p.id != nullptr, has_ns = p.nscat != nullptr;
     // plane order inside a stage: x y z vx vy vz [e] [id] [nscat]
     const int q_e = 6, q_id = 6 + (WAVE ? 1 : 0), q_ns = q_id + (has_id ? 1 : 0);
@@ -163,13 +171,15 @@ pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
         uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
         if (has_ns) nsc = reinterpret_cast<const uint4 *>(base)[q_ns * 32 + lane];
         __syncwarp();  // every lane has read its operands: the stage may be refilled
-        pcl_step_group4<WAVE, DEL, false>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, zero4, zero4, zero4, cnt);
+        pcl_step_group4_masked<WAVE, DEL, false, false, PL>(p, K, s_tab, i, x, y, z, vx, vy, vz, e, id, nsc, zero4, zero4, zero4, s_acc, true);
     }
-    // slots past the last full warp-tile: register path, block 0 only (< 128 slots)
+    // slots past the last full warp-tile: register path, block 0 only (< 128 slots), whole warps at a time
     if (blockIdx.x == 0) {
         const uint64_t nvec = valid / 4;
-        for (uint64_t g = ntiles * 32 + threadIdx.x; g < nvec; g += PCL_BLOCK) {
-            const uint64_t i = g * 4;
+        for (uint64_t g0 = ntiles * 32 + (threadIdx.x & ~31u); g0 < nvec; g0 += PCL_BLOCK) {
+            const uint64_t g = g0 + lane;
+            const bool in = g < nvec;
+            const uint64_t i = (in ? g : g0) * 4;
             float4 x = pcl_ld4(p.x + i), y = pcl_ld4(p.y + i), z = pcl_ld4(p.z + i);
             float4 vx = pcl_ld4(p.vx + i), vy = pcl_ld4(p.vy + i), vz = pcl_ld4(p.vz + i);
             float4 e = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -178,49 +188,31 @@ pcl_k_photon_step_tma(pcl_soa p, StepK K, int64_t *row) {
             if (has_id) id = pcl_ld4u(p.id + i);
             uint4 nsc = make_uint4(0u, 0u, 0u, 0u);
             if (has_ns) nsc = pcl_ld4u(p.nscat + i);
-            pcl_step_group4<WAVE, DEL, false>(p, K, i, x, y, z, vx, vy, vz, e, id, has_id, nsc, zero4, zero4, zero4, cnt);
+            if (!in) x.x = x.y = x.z = x.w = __int_as_float(0x7fc00000);
+            pcl_step_group4_masked<WAVE, DEL, false, false, PL>(p, K, s_tab, i, x, y, z, vx, vy, vz, e, id, nsc, zero4, zero4, zero4, s_acc, in);
         }
-        pcl_step_tail<WAVE, DEL, false>(p, K, nvec * 4, cnt);
+        pcl_step_tail<WAVE, DEL, false, false, PL>(p, K, s_tab, nvec * 4, s_acc);
     }
-    pcl_flush_tally(cnt, row, K.nplanes);
+    __syncthreads();
+    pcl_row_to_global(s_acc, row);
 }
 
 // scalar form for views that are not 16-byte aligned
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
-    constexpr int NC = PL ? C_N : C_PLANE0;
-    uint32_t cnt[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) cnt[q] = 0u;
+    __shared__ __align__(16) unsigned char s_tab[DEL ? 16 : PCL_TRIG_BYTES];
+    __shared__ unsigned int s_acc[C_N];
+    if (threadIdx.x < C_N) s_acc[threadIdx.x] = 0u;
+    if (!DEL) pcl_trig_to_shared(s_tab, K.trig);
+    else __syncthreads();
     const uint64_t end = pcl_valid_slots(p);
     const uint64_t begin = aligned ? (end / 4) * 4 : 0;
     const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
-    for (uint64_t i = begin + (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < end; i += stride) {
-        float x = p.x[i];
-        if (x != x) continue;
-        float y = p.y[i], z = p.z[i], vx = p.vx[i], vy = p.vy[i], vz = p.vz[i];
-        float ut, up, ur;
-        if (INJ) {
-            ut = K.u_theta[i];
-            up = K.u_phi[i];
-            ur = K.u_rand[i];
-        } else {
-            uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-            pcl_draw(K, gid, ut, up, ur);
-        }
-        uint32_t f = pcl_photon_one<WAVE, DEL>(K, x, y, z, vx, vy, vz, WAVE ? p.e[i] : 1.f, ut, up, ur, cnt);
-        p.x[i] = x;
-        p.y[i] = y;
-        p.z[i] = z;
-        if (!DEL && (f & F_SCATTERED)) {
-            p.vx[i] = vx;
-            p.vy[i] = vy;
-            p.vz[i] = vz;
-            if (p.nscat) p.nscat[i] += 1u;
-        }
-    }
-    pcl_flush_tally(cnt, row, K.nplanes);
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < end; i += stride)
+        pcl_step_scalar<WAVE, DEL, INJ, false, PL>(p, K, s_tab, i, s_acc);
+    __syncthreads();
+    pcl_row_to_global(s_acc, row);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,26 +230,6 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 // Traffic per live photon and launch: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
 // !COMPACT: in place; r is always written, v and nscat only by groups in which a photon scattered.
 // ---------------------------------------------------------------------------------------------
-// Per-timestep tally flush of a warp.  A thread owns 4 photons, so a counter is at most 4 per thread and at most
-// 128 per warp: four counters travel as 8-bit fields of one word through ONE warp reduction (the fields cannot carry
-// into each other), and lane q then adds counter q to the CTA's row with a single predicated shared-memory atomic.
-// (One reduction, a leader election and a branch per counter used to cost 136 of the 872 instructions a thread
-// executes per timestep.)
-template <int NC>
-__device__ __forceinline__ void pcl_tally_to_shared(const uint32_t (&cnt)[NC], unsigned int *acc, uint32_t nplanes) {
-    static_assert(NC % 4 == 0 && NC <= 32, "counters are packed four to a word, one lane per counter");
-    (void)nplanes;  // columns of planes that are not configured are never incremented
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t mine = 0u;
-#pragma unroll
-    for (int g = 0; g < NC / 4; ++g) {
-        const uint32_t packed = cnt[4 * g] | (cnt[4 * g + 1] << 8) | (cnt[4 * g + 2] << 16) | (cnt[4 * g + 3] << 24);
-        const uint32_t w = __reduce_add_sync(0xffffffffu, packed);
-        if ((lane >> 2) == (uint32_t)g) mine = (w >> (8u * (lane & 3u))) & 0xffu;
-    }
-    if (lane < (uint32_t)NC && mine) atomicAdd(&acc[lane], mine);
-}
-
 #ifndef PCL_MULTI_MINB_COMPACT
 #define PCL_MULTI_MINB_COMPACT 4
 #endif
@@ -267,21 +239,23 @@ __device__ __forceinline__ void pcl_tally_to_shared(const uint32_t (&cnt)[NC], u
 template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
 __global__ void __launch_bounds__(PCL_BLOCK, COMPACT ? PCL_MULTI_MINB_COMPACT : PCL_MULTI_MINB_INPLACE)
 pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
-    constexpr int NC = PL ? C_N : C_PLANE0;
     constexpr int NST = COMPACT ? 9 : 1;  // staged planes: x y z vx vy vz id nscat e
-    __shared__ float s_stage[NST][COMPACT ? PCL_BLOCK * 4 : 1];
+    __shared__ __align__(16) float s_stage[NST][COMPACT ? PCL_BLOCK * 4 + 32 : 4];
     __shared__ uint32_t s_warp[PCL_WARPS];
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_acc[PCL_FUSE_MAX][C_N];
+    __shared__ __align__(16) unsigned char s_tab[DEL ? 16 : PCL_TRIG_BYTES];
     for (uint32_t q = threadIdx.x; q < PCL_FUSE_MAX * C_N; q += PCL_BLOCK) (&s_acc[0][0])[q] = 0u;
-    __syncthreads();
+    if (!DEL) pcl_trig_to_shared(s_tab, K.trig);
+    else __syncthreads();
     const uint64_t n = pcl_valid_slots(s);
     const uint64_t ntiles = (n + PCL_BLOCK * 4 - 1) / (PCL_BLOCK * 4);
-    const bool has_id = s.id != nullptr;
+    const bool has_id = s.id != nullptr, has_ns = s.nscat != nullptr;
     // the e plane travels with the survivors whenever both sides have one, also when the law does not read it
     // (a photon keeps its energy through delete scattering and the escape sphere: light.py:34)
     const bool carry_e = COMPACT && !WAVE && s.e != nullptr && d.e != nullptr;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base_lo = (uint32_t)s.id_base;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t i = (tile * PCL_BLOCK + threadIdx.x) * 4;
         float4 x, y, z, vx, vy, vz, e = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -325,34 +299,26 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
                 }
             }
         }
-        uint32_t any_scat = 0u;
+        bool any_scat = false;
         for (uint32_t st = 0; st < nsteps; ++st) {
             // all four photons of every lane of this warp retired: nothing left to do for the warp
             const bool alive = (x.x == x.x) || (x.y == x.y) || (x.z == x.z) || (x.w == x.w);
             if (!__any_sync(0xffffffffu, alive)) break;
-            uint32_t cnt[NC];
+            pcl_draw3 dr[4];
 #pragma unroll
-            for (int q = 0; q < NC; ++q) cnt[q] = 0u;
-            float ut[4], up[4], ur[4];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {  // four independent Philox chains: the compiler interleaves them
-                if (INJ) {
-                    ut[l] = pcl_f4(ut4, l);
-                    up[l] = pcl_f4(up4, l);
-                    ur[l] = pcl_f4(ur4, l);
-                } else {
-                    pcl_draw_at(K, K.step + st, s.id_base + (uint64_t)pcl_u4(id, l), ut[l], up[l], ur[l]);
-                }
-            }
+            for (int l = 0; l < 4; ++l)  // four independent Philox chains: the compiler interleaves them
+                dr[l] = INJ ? pcl_draw_floats(pcl_f4(ut4, l), pcl_f4(up4, l), pcl_f4(ur4, l))
+                            : pcl_draw_at(K, K.step + st, base_lo + pcl_u4(id, l));
+            pcl_tally4 t = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                uint32_t f = pcl_photon_one<WAVE, DEL>(K, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                       pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), ut[l], up[l], ur[l], cnt);
-                const bool sc = !DEL && (f & F_SCATTERED);
-                any_scat |= sc ? 1u : 0u;
+                const bool hit = pcl_photon_one<WAVE, DEL, false, PL>(K, s_tab, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                                      pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), dr[l], t);
+                const bool sc = !DEL && hit;
+                any_scat = any_scat || sc;
                 pcl_u4(nsc, l) += sc ? 1u : 0u;
             }
-            pcl_tally_to_shared(cnt, s_acc[st], K.nplanes);
+            pcl_tally_to_shared<PL>(t, s_acc[st]);
         }
         if (!COMPACT) {
             if (full) {
@@ -412,8 +378,15 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             tot += t;
         }
         if (threadIdx.x == 0) s_base = tot ? atomicAdd(n_out, (unsigned long long)tot) : 0ull;
-        // stage the survivors, plane by plane, at their tile-local rank
-        uint32_t rk = wbase + (inc - c);
+        __syncthreads();
+        // The tile's output range [base, base + tot) starts anywhere.  Survivors are staged at their rank PLUS
+        // skew = base mod 32, so that stage index q and output slot (base - skew) + q have the same alignment:
+        // the copy-out then moves 16 bytes per thread and plane (LDS.128 -> STG.128), every warp store covers
+        // whole 128-byte lines of the output (full lines in HBM, full-size packets when `d` is host memory),
+        // and only the few threads on the two edges of the range fall back to scalar stores.
+        const unsigned long long base = s_base;
+        const uint32_t skew = (uint32_t)(base & 31ull);
+        uint32_t rk = skew + wbase + (inc - c);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             if (!(keep & (1u << l))) continue;
@@ -424,29 +397,41 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             s_stage[4][rk] = pcl_f4(vy, l);
             s_stage[5][rk] = pcl_f4(vz, l);
             s_stage[6][rk] = __uint_as_float(pcl_u4(id, l));
-            s_stage[7][rk] = __uint_as_float(pcl_u4(nsc, l));
+            if (has_ns) s_stage[7][rk] = __uint_as_float(pcl_u4(nsc, l));
             if (WAVE || carry_e) s_stage[NST - 1][rk] = pcl_f4(e, l);
             ++rk;
         }
         __syncthreads();
-        // coalesced copy-out: consecutive threads write consecutive survivors, and every warp store
-        // covers one 128-byte ALIGNED line of the output (the tile's range starts anywhere, so the first
-        // lanes of the first line idle): full lines in HBM, full-size packets when `d` is host memory
-        const unsigned long long base = s_base;
-        const uint32_t skew = (uint32_t)(base & 31ull);
-        for (uint32_t qq = threadIdx.x; qq < tot + skew; qq += PCL_BLOCK) {
-            if (qq < skew) continue;
-            const uint32_t q = qq - skew;
-            const unsigned long long o = base + q;
-            d.x[o] = s_stage[0][q];
-            d.y[o] = s_stage[1][q];
-            d.z[o] = s_stage[2][q];
-            d.vx[o] = s_stage[3][q];
-            d.vy[o] = s_stage[4][q];
-            d.vz[o] = s_stage[5][q];
-            d.id[o] = __float_as_uint(s_stage[6][q]);
-            if (s.nscat) d.nscat[o] = __float_as_uint(s_stage[7][q]);
-            if (WAVE || carry_e) d.e[o] = s_stage[NST - 1][q];
+        const uint32_t end = skew + tot;
+        const unsigned long long obase = base - skew;  // a multiple of 32 slots
+        for (uint32_t q4 = threadIdx.x * 4; q4 < end; q4 += PCL_BLOCK * 4) {
+            const unsigned long long o = obase + q4;
+            if (q4 >= skew && q4 + 3 < end) {
+                pcl_st4(d.x + o, *reinterpret_cast<const float4 *>(&s_stage[0][q4]));
+                pcl_st4(d.y + o, *reinterpret_cast<const float4 *>(&s_stage[1][q4]));
+                pcl_st4(d.z + o, *reinterpret_cast<const float4 *>(&s_stage[2][q4]));
+                pcl_st4(d.vx + o, *reinterpret_cast<const float4 *>(&s_stage[3][q4]));
+                pcl_st4(d.vy + o, *reinterpret_cast<const float4 *>(&s_stage[4][q4]));
+                pcl_st4(d.vz + o, *reinterpret_cast<const float4 *>(&s_stage[5][q4]));
+                pcl_st4(reinterpret_cast<float *>(d.id) + o, *reinterpret_cast<const float4 *>(&s_stage[6][q4]));
+                if (has_ns) pcl_st4(reinterpret_cast<float *>(d.nscat) + o, *reinterpret_cast<const float4 *>(&s_stage[7][q4]));
+                if (WAVE || carry_e) pcl_st4(d.e + o, *reinterpret_cast<const float4 *>(&s_stage[NST - 1][q4]));
+            } else {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t q = q4 + l;
+                    if (q < skew || q >= end) continue;
+                    d.x[o + l] = s_stage[0][q];
+                    d.y[o + l] = s_stage[1][q];
+                    d.z[o + l] = s_stage[2][q];
+                    d.vx[o + l] = s_stage[3][q];
+                    d.vy[o + l] = s_stage[4][q];
+                    d.vz[o + l] = s_stage[5][q];
+                    d.id[o + l] = __float_as_uint(s_stage[6][q]);
+                    if (has_ns) d.nscat[o + l] = __float_as_uint(s_stage[7][q]);
+                    if (WAVE || carry_e) d.e[o + l] = s_stage[NST - 1][q];
+                }
+            }
         }
         __syncthreads();  // the stage and s_warp are rewritten by the next tile
     }
@@ -465,6 +450,8 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
 template <bool WAVE, bool DEL, bool INJ>
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
+    __shared__ __align__(16) unsigned char s_tab[DEL ? 16 : PCL_TRIG_BYTES];
+    if (!DEL) pcl_trig_to_shared(s_tab, K.trig);
     uint32_t cnt[C_PLANE0];
 #pragma unroll
     for (int q = 0; q < C_PLANE0; ++q) cnt[q] = 0u;
@@ -475,19 +462,12 @@ pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
         int32_t flag = 0;
         if (xx == xx) {
             cnt[C_LIVEIN] += 1u;
-            float ut, up, ur;
-            if (INJ) {
-                ut = K.u_theta[i];
-                up = K.u_phi[i];
-                ur = K.u_rand[i];
-            } else {
-                uint64_t gid = p.id_base + (p.id ? (uint64_t)p.id[i] : i);
-                pcl_draw(K, gid, ut, up, ur);
-            }
+            const pcl_draw3 d = INJ ? pcl_draw_floats(K.u_theta[i], K.u_phi[i], K.u_rand[i])
+                                    : pcl_draw_at(K, K.step, (uint32_t)p.id_base + (p.id ? p.id[i] : (uint32_t)i));
             float vx = 0.f, vy = 0.f, vz = 0.f;
             float e = WAVE ? p.e[i] : 1.f;
-            uint32_t f = pcl_scatter_one<WAVE, DEL>(true, p.dx[i], p.dy[i], p.dz[i], e, ut, up, ur, K.k, K.c, vx, vy, vz);
-            if (f & F_SCATTERED) {
+            const bool hit = pcl_scatter_one<WAVE, DEL>(true, p.dx[i], p.dy[i], p.dz[i], e, d, K, s_tab, vx, vy, vz);
+            if (hit) {
                 flag = 1;
                 cnt[C_SCAT] += 1u;
                 if (DEL) {
@@ -500,7 +480,7 @@ pcl_k_scatter(pcl_soa p, StepK K, int32_t *flags, int64_t *row, uint64_t n) {
                     if (p.nscat) p.nscat[i] += 1u;
                 }
             }
-            if (!(f & F_ABSORBED)) cnt[C_ALIVE] += 1u;
+            if (!(DEL && hit)) cnt[C_ALIVE] += 1u;
         }
         if (flags) flags[i] = flag;
     }
@@ -557,18 +537,39 @@ pcl_k_tally(pcl_soa p, StepK K, int64_t *row, uint64_t n) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// 64 -> 32 bit fold of (seed, high word of the id base, stream) for the Philox2x32 key: splitmix64 finaliser
+static uint32_t pcl_fold_key(uint64_t seed, uint64_t id_hi, uint64_t stream) {
+    uint64_t z = seed ^ (id_hi * 0x9E3779B97F4A7C15ull) ^ (stream << 56);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
 int pcl_fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *sp, const pcl_rng *rng,
-                      float escape_r2, const pcl_planes *planes) {
+                      float escape_r2, const pcl_planes *planes, uint64_t id_base) {
     memset(&K, 0, sizeof(K));
     K.dt = dt;
+    K.trig = ctx->trig;
     if (sp) {
         K.k = sp->k;
         K.c = sp->c;
+        // 1/k in float64, rounded once: k = 0 -> FLT_MAX (only rand = 0 scatters, as pcoll = 0 >= 0 does in the
+        // reference), k < 0 or NaN -> NaN (the test never succeeds), k = inf -> 0 (always)
+        const double kd = (double)sp->k;
+        if (kd > 0.0) {
+            const double inv = 1.0 / kd;
+            K.kinv = inv > 3.4028234663852886e38 ? 3.4028234663852886e38f : (float)inv;
+        } else if (kd == 0.0) {
+            K.kinv = 3.4028234663852886e38f;
+        } else {
+            K.kinv = nanf("");
+        }
     }
-    K.r2_escape = escape_r2;
+    K.r2_escape = escape_r2 > 0.f ? escape_r2 : nanf("");
     if (rng) {
-        K.seed_lo = (uint32_t)rng->seed;
-        K.seed_hi = (uint32_t)(rng->seed >> 32);
+        uint32_t key = pcl_fold_key(rng->seed, id_base >> 32, 0);
+        for (int r = 0; r < 10; ++r) K.rk[r] = key + (uint32_t)r * PCL_PHILOX2_W;
         K.step = rng->step;
         K.u_theta = rng->u_theta;
         K.u_phi = rng->u_phi;
@@ -684,6 +685,8 @@ static int check_photon_view(pcl_ctx *ctx, const pcl_soa *p, const pcl_scatter_p
     PCL_REQUIRE(ctx, p != nullptr && sp != nullptr, "null argument");
     PCL_REQUIRE(ctx, p->x && p->y && p->z && p->vx && p->vy && p->vz, "r and v planes are required");
     PCL_REQUIRE(ctx, p->n < (1ull << 32), "a shard holds fewer than 2^32 slots");
+    // the Philox counter carries the low word of the global id and the key the high word (uniform per launch)
+    PCL_REQUIRE(ctx, (p->id_base & 0xffffffffull) + p->n <= (1ull << 32), "the global ids of a shard must not cross a multiple of 2^32");
     if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
     return 0;
 }
@@ -714,7 +717,7 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
     }
     if (p->n == 0) return 0;
     StepK K;
-    rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes);
+    rc = pcl_fill_stepk(ctx, K, dt, sp, rng, escape_r2, planes, p->id_base);
     if (rc) return rc;
     return photon_dispatch(ctx, st, p, dst, K, sp->mode, tally_row, n_out, nsteps, keep_count);
 }
@@ -815,7 +818,7 @@ extern "C" int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, con
     PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     StepK K;
-    rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr);
+    rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr, p->id_base);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
@@ -857,7 +860,7 @@ extern "C" int pcl_tally(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, const
     PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (p->n == 0) return 0;
     StepK K;
-    int rc = pcl_fill_stepk(ctx, K, 0.f, nullptr, nullptr, 0.f, planes);
+    int rc = pcl_fill_stepk(ctx, K, 0.f, nullptr, nullptr, 0.f, planes, 0);
     if (rc) return rc;
     unsigned grid = pcl_stream_grid(ctx, p->n, PCL_BLOCK, 8);
     pcl_k_tally<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(*p, K, tally_row, p->n);

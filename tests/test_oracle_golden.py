@@ -185,3 +185,49 @@ def test_f32_twin_delete_matches_reference(golden):
         prow = g["plane_rows"][s]
         assert int(row[oracle.T_ALIVE]) == int(prow[1])
         assert int(row[oracle.T_PLANE0]) == int(prow[2])
+
+
+# ---- in-kernel random numbers and directions (NEW relative to the reference: parity unpinned, pinned to the published
+# ---- known-answer vectors of the generator and to libm) -----------------------------------------------------------------
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors (Salmon et al., SC'11 reference implementation): philox4x32-10 feeds the emission sampler,
+    philox2x32-10 the photon steps."""
+    assert oracle.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    assert oracle.philox2x32_10([0, 0], 0) == [0xff1dae59, 0x6cd10df2]
+    assert oracle.philox2x32_10([0xffffffff] * 2, 0xffffffff) == [0x2c3f628b, 0xab4fd7ad]
+    assert oracle.philox2x32_10([0x243f6a88, 0x85a308d3], 0x13198a2e) == [0xdd7ce038, 0xf62a4c12]
+
+
+def test_photon_draws_are_the_philox2x32_block():
+    """u_rand = w0[31:8] / 2^24, u_theta = w1[31:8] / 2^24, u_phi = (w1[7:0] : w0[7:0]) / 2^16 of the block at
+    counter (low id word, step), key = fold(seed, high id word)."""
+    seed, step, base = 0x1234567890abcdef, 7, (3 << 32) + 1000
+    ut, up, ur = oracle.philox_uniforms(5, base, seed, step)
+    for i in range(5):
+        gid = base + i
+        w0, w1 = oracle.philox2x32_10([gid & 0xffffffff, step], oracle.fold_key(seed, gid >> 32))
+        assert ur[i] == np.float32((w0 >> 8) / 2.0 ** 24) and ut[i] == np.float32((w1 >> 8) / 2.0 ** 24)
+        assert up[i] == np.float32((((w1 & 0xff) << 8) | (w0 & 0xff)) / 2.0 ** 16)
+    a = oracle.philox_uniforms(4096, 0, seed, 0)
+    b = oracle.philox_uniforms(4096, 0, seed, 1)
+    c = oracle.philox_uniforms(4096, 0, seed + 1, 0)
+    for q in range(3):  # distinct steps and seeds give unrelated streams; uniforms are uniform
+        assert not np.array_equal(a[q], b[q]) and not np.array_equal(a[q], c[q])
+        assert abs(float(a[q].mean()) - 0.5) < 0.03 and 0.0 <= a[q].min() and a[q].max() < 1.0
+
+
+def test_direction_table_matches_libm():
+    """sin/cos by table + addition theorem (what the kernels and the binary32 twin evaluate) against float64 libm."""
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(20000):
+        k8, f = int(rng.integers(0, 256)), float(rng.random())
+        for entry, scale in ((2 * k8, 2 * np.pi / 256), (k8, np.pi / 256)):
+            b = np.float32(f) * np.float32(scale)
+            s, c = oracle.sincos_tab(entry, b)
+            ang = 2 * np.pi * entry / 512 + float(b)
+            worst = max(worst, abs(s - np.sin(ang)), abs(c - np.cos(ang)))
+    assert worst < 2.5e-7, worst
