@@ -96,6 +96,13 @@ class Object:
             setattr(self, attr, val)
 
 
+class _Probe:
+    """Records whether an exit predicate looked at device-side state (particles, measure-step rows) while it was
+    evaluated: predicates that only read ``t`` / ``dt`` / ``ts`` can be evaluated ahead of the device."""
+
+    touched = False
+
+
 class _ObjectList(list):
     """``sim.objects``: a list that knows when the device store is the authority.
 
@@ -139,6 +146,9 @@ class _ObjectList(list):
 
     def __len__(self):
         sim = self._sim
+        _Probe.touched = True
+        if sim._len_override is not None:  # replay of an exit predicate against the tally row of an earlier timestep
+            return sim._len_override
         if sim._device_dirty and sim.store is not None:
             return sim._device_live_count()
         n = super().__len__()
@@ -150,10 +160,12 @@ class _ObjectList(list):
         return n
 
     def __iter__(self):
+        _Probe.touched = True
         self._sim._pull_objects()
         return super().__iter__()
 
     def __getitem__(self, i):
+        _Probe.touched = True
         self._sim._pull_objects()
         return super().__getitem__(i)
 
@@ -193,6 +205,7 @@ class Simulation(threading.Thread):
         self._host_dirty = True
         self._device_dirty = False
         self._pending = None  # bulk particles registered with add_particles()
+        self._len_override = None
         self.objects = _ObjectList(self)
         self.steps = {}
         self._state_lock = threading.Lock()
@@ -403,18 +416,21 @@ class Simulation(threading.Thread):
         self.t = 0
         self.dt = 0
         self.ts = []
-        self.step_index = 0
-        self.running = True
+        self.running = True  # step_index is NOT reset: it is the Philox step counter and must never repeat
         try:
             plan = self._plan()
-            while not self.exit(self):
-                with self._state_lock:
-                    for step in plan:
-                        if not step.uses_device and getattr(step, "touches_objects", True):
-                            self._pull_objects()
-                            self._host_dirty = self._host_dirty or self.store is not None
-                        step.run(self)
-                    self.step_index += 1
+            fast = self._bulk_plan(plan)
+            if fast is not None:
+                self._run_chunked(*fast)
+            else:
+                while not self.exit(self):
+                    with self._state_lock:
+                        for step in plan:
+                            if not step.uses_device and getattr(step, "touches_objects", True):
+                                self._pull_objects()
+                                self._host_dirty = self._host_dirty or self.store is not None
+                            step.run(self)
+                        self.step_index += 1
             with self._state_lock:
                 for step in self.steps.values():
                     step.terminate(self)
@@ -423,6 +439,106 @@ class Simulation(threading.Thread):
         finally:
             self.run_time = time.time() - self.start_time
             self.running = False
+
+    # ---- chunked form of the main loop ------------------------------------------------------------------
+    def _bulk_plan(self, plan):
+        """(UpdateTimeStep, fused step) when the whole plan is that pair and the fused step can advance several
+        timesteps per C-ABI call; None otherwise."""
+        if (self.cl_on and len(plan) == 2 and type(plan[0]) is UpdateTimeStep and hasattr(plan[1], "run_many")
+                and plan[1].can_run_many(self)):
+            return plan[0], plan[1]
+        return None
+
+    def _advance(self, upd, fused, k, probe_exit=False):
+        """Up to k timesteps: UpdateTimeStep on the host (stopping early when dt changes or, with ``probe_exit``, when
+        the exit predicate fires or starts looking at the particles), then ONE bulk call for all of them.
+        Returns the (t, dt) of every timestep done."""
+        dts, ts = [], []
+        while len(dts) < k:
+            upd.run(self)
+            dts.append(float(self.dt))
+            ts.append(self.t)
+            if dts[-1] != dts[0]:
+                break
+            if probe_exit and len(dts) < k:
+                _Probe.touched = False
+                if self.exit(self) or _Probe.touched:
+                    break
+        if dts[-1] != dts[0]:  # dt changed inside the chunk: these timesteps go one by one
+            for dt_i, t_i in zip(dts, ts):
+                fused.run_many(self, 1, dt_i, [t_i])
+                self.step_index += 1
+        else:
+            fused.run_many(self, len(dts), dts[0], ts)
+            self.step_index += len(dts)
+        return list(zip(ts, dts))
+
+    def _run_chunked(self, upd, fused):
+        """``while not exit(sim): one timestep`` (physicl/__init__.py:512-516) in chunks of timesteps, stopping at
+        EXACTLY the timestep the per-step loop would stop at.
+
+        A predicate that only reads ``t`` / ``dt`` / ``ts`` (``t >= 0.1``, reference test/test_light.py:20) is evaluated
+        ahead of the device: after every host-side UpdateTimeStep of the chunk the predicate is asked again, and the
+        timesteps counted that way go to the device in one call.  A predicate that looks at the particles
+        (``len(objects) == 0``, the reference's default, physicl/__init__.py:414) is checked AFTER the chunk, against
+        the tally row of every timestep in it; if it fired early the chunk is rolled back to a device-side copy taken
+        before it and re-run up to the firing timestep (the draws are a pure function of particle id and step index,
+        so the re-run reproduces those timesteps bit for bit)."""
+        while True:
+            _Probe.touched = False
+            if self.exit(self):
+                return
+            looks_at_particles = _Probe.touched
+            kmax = max(1, min(fused.chunk_steps(self), 256))
+            with self._state_lock:
+                if not looks_at_particles:
+                    self._advance(upd, fused, kmax, probe_exit=True)
+                elif not getattr(fused, "tallies_every_timestep", False):
+                    self._advance(upd, fused, 1)  # no per-timestep rows to replay the predicate against
+                else:
+                    ck = self._checkpoint(fused)
+                    done = self._advance(upd, fused, kmax)
+                    fire = self._first_fire(ck, done)
+                    if fire is not None:
+                        self._rollback(fused, ck)
+                        self._advance(upd, fused, fire)
+
+    def _checkpoint(self, fused):
+        st = self.device_store()
+        return {"t": self.t, "dt": self.dt, "nts": len(self.ts), "step_index": self.step_index,
+                "store": st.checkpoint("photon"), "rows": st.current_row, "members": fused.checkpoint()}
+
+    def _rollback(self, fused, ck):
+        self.t, self.dt, self.step_index = ck["t"], ck["dt"], ck["step_index"]
+        del self.ts[ck["nts"]:]
+        self.store.restore("photon", ck["store"])
+        fused.rollback(ck["members"])
+
+    def _first_fire(self, ck, done):
+        """Number of timesteps of the chunk after which the exit predicate first holds (None: not inside the chunk),
+        evaluated with t, dt, ts and len(objects) as they were after each timestep."""
+        from . import _capi
+
+        st = self.store
+        first = ck["rows"] + 1
+        alive = np.array([int(st.read_row(first + j)[_capi.T_ALIVE]) for j in range(len(done))], np.int64)
+        if self.shard:
+            from .dist import all_reduce_rows
+
+            alive = all_reduce_rows(alive)
+        full_ts, end = self.ts, (self.t, self.dt)
+        try:
+            for j, (t_j, dt_j) in enumerate(done[:-1]):
+                self.t, self.dt = t_j, dt_j
+                self.ts = full_ts[:ck["nts"] + j + 1]
+                self._len_override = int(alive[j])
+                if self.exit(self):
+                    return j + 1
+        finally:
+            self._len_override = None
+            self.ts = full_ts
+            self.t, self.dt = end
+        return None
 
     def join(self, timeout=None):
         super().join(timeout)
@@ -437,29 +553,13 @@ class Simulation(threading.Thread):
         if not self.ts:
             self.t, self.dt = 0, 0
         nsteps = int(nsteps)
-        # bulk form: [UpdateTimeStep, fused photon step] with a constant dt goes to the device in
-        # chunks of about feedback_every timesteps per C-ABI call (a whole number of compaction periods)
-        if (len(plan) == 2 and type(plan[0]) is UpdateTimeStep and hasattr(plan[1], "run_many")
-                and plan[1].can_run_many(self)):
-            upd, fused = plan
+        # bulk form: [UpdateTimeStep, fused step] goes to the device in chunks of about feedback_every timesteps per
+        # C-ABI call (a whole number of compaction periods)
+        fast = self._bulk_plan(plan)
+        if fast is not None:
+            upd, fused = fast
             while nsteps > 0:
-                k = min(nsteps, fused.chunk_steps(self), 256)
-                dts, ts = [], []
-                for _ in range(k):
-                    upd.run(self)
-                    dts.append(float(self.dt))
-                    ts.append(self.t)
-                    if dts[-1] != dts[0]:
-                        break
-                if dts[-1] != dts[0]:  # dt changed inside the chunk: finish these steps one by one
-                    for dt_i, t_i in zip(dts, ts):
-                        fused.run_many(self, 1, dt_i, [t_i])
-                        self.step_index += 1
-                    nsteps -= len(dts)
-                    continue
-                fused.run_many(self, k, dts[0], ts)
-                self.step_index += k
-                nsteps -= k
+                nsteps -= len(self._advance(upd, fused, min(nsteps, fused.chunk_steps(self), 256)))
             return
         for _ in range(nsteps):
             for step in plan:

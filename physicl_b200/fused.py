@@ -36,6 +36,7 @@ from . import _capi, light, newton
 
 class FusedPhotonStep(physicl.Step):
     uses_device = True
+    tallies_every_timestep = True  # one tally row per timestep: Simulation._run_chunked can replay exit predicates
 
     def __init__(self, kin, scatter, escape, measures):
         self.kin, self.scatter, self.escape, self.measures = kin, scatter, escape, measures
@@ -119,6 +120,22 @@ class FusedPhotonStep(physicl.Step):
                 # two levels are enough (measured flat between 4 and 8 at d = 6.5 %, section 4 of DESIGN.md), and a
                 # stale estimate then costs a few per cent at worst
                 self.cadence = 8 if died / live_in < 0.02 else 4
+            self._fb_pool.append(buf)
+
+    # ---- roll-back support for Simulation._run_chunked ------------------------------------------------
+    def checkpoint(self):
+        return {"escape": len(self.escape._rows) if self.escape else 0, "measures": [len(m._pending) for m in self.measures],
+                "cadence": self.cadence}
+
+    def rollback(self, ck):
+        if self.escape:
+            del self.escape._rows[ck["escape"]:]
+        for m, n in zip(self.measures, ck["measures"]):
+            del m._pending[n:]
+        self.cadence = ck["cadence"]
+        while self._fb:  # feedback of the discarded timesteps must not shrink the restored slot count
+            ev, buf, _ = self._fb.pop()
+            ev.synchronize()
             self._fb_pool.append(buf)
 
     # ---- k timesteps with one C-ABI call ----------------------------------------------------------

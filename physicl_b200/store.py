@@ -248,6 +248,30 @@ class DeviceParticleStore:
             g.n_exact = True
         return None if g is None else g.n
 
+    # ---- device-side copies (Simulation._run_chunked rolls a chunk of timesteps back to one) ------------
+    def checkpoint(self, kind="photon"):
+        g = self.groups.get(kind)
+        if g is None:
+            return None
+        n = max(g.n, 1)
+        return {"planes": {nm: t[:n].clone() for nm, t in g.planes.items()}, "cur": g.cur, "id_valid": list(g.id_valid),
+                "n": g.n, "n_exact": g.n_exact, "n_live": g.n_live, "n_dev": None if g.n_dev is None else g.n_dev.clone()}
+
+    def restore(self, kind, ck):
+        if ck is None:
+            return
+        g = self.groups[kind]
+        g.cur, g.id_valid, g.n, g.n_exact, g.n_live = ck["cur"], list(ck["id_valid"]), ck["n"], ck["n_exact"], ck["n_live"]
+        for nm, t in ck["planes"].items():
+            if nm in g.planes and g.planes[nm].numel() >= t.numel():
+                g.planes[nm][: t.numel()].copy_(t)
+            else:
+                g.planes[nm] = t.clone()
+        for nm in [nm for nm in g.planes if nm not in ck["planes"]]:
+            del g.planes[nm]
+        if ck["n_dev"] is not None:
+            g.n_dev.copy_(ck["n_dev"])
+
     # ---- compaction -------------------------------------------------------------------------
     def reserve_spare(self, kind="photon"):
         """Allocate the ping-pong partner planes and the device-side slot counters now (pipelines that

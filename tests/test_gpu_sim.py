@@ -249,7 +249,8 @@ def test_bulk_run_steps_equals_threaded_run():
     assert np.array_equal(pa["id"], pb["id"])
     for nm in ("x", "y", "z", "vx", "vy", "vz"):
         assert np.array_equal(pa[nm].view(np.uint32), pb[nm].view(np.uint32)), nm
-    assert x.cl_ctx.launches <= a.cl_ctx.launches
+    # the threaded run is chunked too (Simulation._run_chunked): both need about one launch per 4-8 timesteps
+    assert x.cl_ctx.launches <= 14 and a.cl_ctx.launches <= 14
 
 
 def _sphere_run(n, steps, seed, A, nd, R, dt=0.001):
@@ -673,3 +674,92 @@ def test_gravity_step_sees_a_rebuilt_store():
     x.run_steps(1)
     snap = x.store.snapshot("object")
     assert abs(snap["x"][0] - 50.0) < 1.0  # the edit was not overwritten by a stale packed array
+
+
+# ---- Simulation.start(): the chunked main loop stops where the per-timestep loop stops ------------------------------
+def _threaded(exit_fn, n=30000, feedback_every=64, delete=False, seed=17, dt_fn=None):
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+    x = phys.Simulation(cl_on=True, exit=exit_fn, seed=seed)
+    x.feedback_every = feedback_every
+    x.add_particles(r, v)
+    x.add_step(0, phys.UpdateTimeStep(dt_fn or (lambda s: np.double(0.001))))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    if delete:
+        x.add_step(2, phys.light.ScatterDeleteStep(np.double(1e-3), np.double(1e-3)))
+    else:
+        x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+        x.add_step(3, phys.light.EscapeSphereStep(1.5e6))
+    sign = phys.light.ScatterSignMeasureStep(None, True)
+    x.add_step(4, sign)
+    x.start()
+    x.join()
+    return x, np.array(sign.data)
+
+
+@pytest.mark.parametrize("case", ["time", "steps", "empty", "half", "time_and_count"])
+def test_chunked_run_stops_exactly_where_the_stepwise_run_stops(case):
+    """reference physicl/__init__.py:512-516 evaluates exit(sim) before EVERY timestep.  The chunked loop (64 timesteps per
+    C-ABI call) must produce the same rows, the same t / ts and the same particles as the same run advanced one timestep
+    per chunk, for predicates on time, on the step count and on the particle count (the latter fire in the middle of a
+    chunk and force a roll-back)."""
+    n = 30000
+    exit_fn = {
+        "time": lambda s: s.t >= 0.0375,
+        "steps": lambda s: len(s.ts) >= 71,
+        "empty": lambda s: len(s.objects) == 0,
+        "half": lambda s: len(s.objects) <= n // 8,
+        "time_and_count": lambda s: s.t >= 0.0105 and len(s.objects) <= (9 * n) // 10,
+    }[case]
+    delete = case in ("empty", "half")
+    a, rows_a = _threaded(exit_fn, n, feedback_every=64, delete=delete)
+    b, rows_b = _threaded(exit_fn, n, feedback_every=1, delete=delete)
+    assert rows_a.shape == rows_b.shape and rows_a.shape[0] >= 3
+    assert np.array_equal(rows_a[:, 1:], rows_b[:, 1:])
+    np.testing.assert_allclose(rows_a[:, 0].astype(float), rows_b[:, 0].astype(float), rtol=0, atol=0)
+    assert len(a.ts) == len(b.ts) == rows_a.shape[0] and float(a.t) == float(b.t)
+    assert a.step_index == b.step_index == rows_a.shape[0]
+    assert a.exit(a) and b.exit(b)
+    if case == "half":  # the stepwise loop stops at the FIRST timestep with <= n/8 photons: the row before is above
+        assert rows_a[-1, 1] <= n // 8 < rows_a[-2, 1]
+    sa, sb = a.store.snapshot("photon"), b.store.snapshot("photon")
+    assert np.array_equal(sa["id"], sb["id"])
+    for k in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(sa[k].view(np.uint32), sb[k].view(np.uint32)), k
+
+
+def test_chunked_run_with_a_time_step_that_changes():
+    """UpdateTimeStep's fn may return a different dt every timestep (physicl/__init__.py:337-343): chunks break there."""
+    dt_fn = lambda s: np.double(0.001 if len(s.ts) % 7 else 0.002)  # noqa: E731
+    a, rows_a = _threaded(lambda s: len(s.ts) >= 30, 20000, feedback_every=64, dt_fn=dt_fn)
+    b, rows_b = _threaded(lambda s: len(s.ts) >= 30, 20000, feedback_every=1, dt_fn=dt_fn)
+    assert rows_a.shape[0] == 30 and np.array_equal(rows_a, rows_b)
+    assert [float(t) for t in a.ts] == [float(t) for t in b.ts]
+
+
+def test_start_after_run_steps_continues_the_random_stream():
+    """run() resets t / dt / ts like the reference (physicl/__init__.py:508-510) but never the Philox step counter."""
+    n = 20000
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = float(phys.light.c)
+
+    def build():
+        x = phys.Simulation(cl_on=True, exit=lambda s: len(s.ts) >= 6, seed=3)
+        x.add_particles(r, v)
+        x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+        x.add_step(1, phys.newton.NewtonianKinematicsStep())
+        x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+        sign = phys.light.ScatterSignMeasureStep(None, True)
+        x.add_step(3, sign)
+        return x, sign
+
+    a, sa = build()
+    a.run_steps(5)
+    a.start()
+    a.join()
+    b, sb = build()
+    b.run_steps(11)
+    assert a.step_index == b.step_index == 11
+    assert np.array_equal(np.array(sa.data)[:, 1:], np.array(sb.data)[:, 1:])
