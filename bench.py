@@ -17,7 +17,8 @@ BASELINE configs, each with its own roofline: photon_sphere_16m (configs[1]), ki
 0.70-of-HBM target refers to), wavelength_64m (configs[2]), gravity_256k (configs[3]).
 
   value      state resident in HBM; CUDA events around the K timesteps of each leg, queued behind a
-             device-side gate (pcl_stream_gate) so that no host launch latency lies between the events
+             device-side gate (pcl_stream_gate) so that no host launch latency lies between the events;
+             the photon legs are driven by sim.start() / sim.join() (the reference's entry point)
   e2e        photon leg through the host-buffer C-ABI entry point with the particle planes in pinned HOST
              memory between calls (H2D + kernel + D2H inside the timed region, host wall clock)
   roofline   dominant kernel (kinematics): algorithmic bytes / launch time
@@ -438,6 +439,15 @@ def photon_sim(n, rank, local, id_base=None):
     return sim, esc, sign
 
 
+def run_threaded(sim, steps):
+    """The timed timesteps go through the reference's own entry point: sim.start() ... sim.join() with an exit predicate
+    on the step count (physicl/__init__.py:501-524; test/test_light.py:36-37).  The warm-up before it used run_steps
+    (a Simulation thread can be started once); the Philox step counter carries on."""
+    sim.exit = lambda s: len(s.ts) >= steps
+    sim.start()
+    sim.join()
+
+
 def photon_roofline(live, scat, ms, wave, kernel):
     """The fused photon kernel is bound by instruction issue, not by DRAM (ncu: profiles/README.md).  `achieved` is
     the warp-instruction issue rate implied by the measured instructions per photon-step of the shipped build."""
@@ -478,7 +488,7 @@ def leg_photon(args, rank, world, local, n, id_base, clocks, prime=True, strong=
         sim.run_steps(args.warmup)
         state["row0"] = store.current_row + 1
 
-    ms, launches, _ = timed_region(world, ctx, local, lambda: sim.run_steps(args.steps), clocks, warm)
+    ms, launches, _ = timed_region(world, ctx, local, lambda: run_threaded(sim, args.steps), clocks, warm)
     rows = np.array([store.read_row(r) for r in range(state["row0"], store.current_row + 1)])
     assert rows.shape[0] == args.steps, rows.shape
     live = float(rows[:, _capi.T_LIVE_IN].sum())
@@ -807,7 +817,7 @@ def bench_wavelength(args, rank, world, local, clocks):
         sim.run_steps(args.warmup)
         state["row0"] = store.current_row + 1
 
-    ms, launches, _ = timed_region(world, ctx, local, lambda: sim.run_steps(args.steps), clocks, warm)
+    ms, launches, _ = timed_region(world, ctx, local, lambda: run_threaded(sim, args.steps), clocks, warm)
     rows = np.array([store.read_row(q) for q in range(state["row0"], store.current_row + 1)])
     live, scat = float(rows[:, _capi.T_LIVE_IN].sum()), float(rows[:, _capi.T_SCATTERED].sum())
     rows_all = sum_rows_over_ranks(rows, world)

@@ -218,3 +218,12 @@ def gravity_f64(pos, m, G, eps2, i_offset=0, n_local=None):
     lib().orc_gravity_f64(C.c_uint64(n_local), C.c_uint64(i_offset), C.c_uint64(N), *[_p(pos[i], np.float64) for i in range(3)],
                           _p(m, np.float64), C.c_double(G), C.c_double(eps2), *[_p(acc[i], np.float64) for i in range(3)])
     return acc
+
+
+def gravity_pick_f64(pos, m, G, eps2, idx):
+    """Accelerations of the bodies ``idx`` from ALL bodies (float64 definition); returns (3, len(idx))."""
+    idx = np.ascontiguousarray(idx, np.uint64)
+    acc = np.empty((3, idx.size))
+    lib().orc_gravity_pick_f64(C.c_uint64(idx.size), _p(idx, np.uint64), C.c_uint64(m.size), *[_p(pos[i], np.float64) for i in range(3)],
+                               _p(m, np.float64), C.c_double(G), C.c_double(eps2), *[_p(acc[i], np.float64) for i in range(3)])
+    return acc

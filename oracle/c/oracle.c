@@ -561,6 +561,27 @@ void orc_gravity_f64(uint64_t n_local, uint64_t i_offset, uint64_t n_total, cons
     }
 }
 
+/* the same definition for an arbitrary list of i-bodies (full-size spot checks) */
+void orc_gravity_pick_f64(uint64_t n_pick, const uint64_t *idx, uint64_t n_total, const double *px, const double *py,
+                          const double *pz, const double *m, double G, double eps2, double *ax, double *ay, double *az) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t q = 0; q < (int64_t)n_pick; ++q) {
+        const uint64_t i = idx[q];
+        double sx = 0, sy = 0, sz = 0;
+        for (uint64_t j = 0; j < n_total; ++j) {
+            double dx = px[j] - px[i], dy = py[j] - py[i], dz = pz[j] - pz[i];
+            double r2 = dx * dx + dy * dy + dz * dz + eps2;
+            double inv = 1.0 / (r2 * sqrt(r2));
+            sx += m[j] * dx * inv;
+            sy += m[j] * dy * inv;
+            sz += m[j] * dz * inv;
+        }
+        ax[q] = G * sx;
+        ay[q] = G * sy;
+        az[q] = G * sz;
+    }
+}
+
 int orc_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

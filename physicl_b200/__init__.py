@@ -418,6 +418,10 @@ class Simulation(threading.Thread):
         self.ts = []
         self.running = True  # step_index is NOT reset: it is the Philox step counter and must never repeat
         try:
+            if self.cl_on:  # the simulation thread is a new host thread: its current CUDA device is 0 until told otherwise
+                import torch
+
+                torch.cuda.set_device(self.device)
             plan = self._plan()
             fast = self._bulk_plan(plan)
             if fast is not None:

@@ -21,7 +21,7 @@ SCATTER_WAVELENGTH, SCATTER_DELETE = 1, 2
 # bench.py turns them into the issue-rate roofline of the photon workloads
 PHOTON_INSTR_PER_STEP = 97.6  # profiles/r2/ncu_full_photon_multi_v2.csv, launch 6: 255.87 M warp instructions / (5 x 16 Mi photon-steps) x 32
 PHOTON_INSTR_PER_STEP_WAVE = 102.0  # static count of the in-place loop (scripts/sass_loop.py); ncu capture pending
-GRAVITY_KERNEL = "pcl_k_gravity_x2<2,128,512>"
+GRAVITY_KERNEL = "pcl_k_gravity_x2<2,128,512,UM,8> (2 i-bodies per thread, 512-body j-tiles, packed FP32; UM = equal masses)"
 
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
@@ -94,6 +94,7 @@ _PROTOS = {
     "pcl_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(Soa), C.c_void_p]),
     "pcl_planck_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "pcl_gravity_accel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
+    "pcl_gravity_accel_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
     "pcl_gravity_kick_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcl_photon_step_host": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64]),
     "pcl_photon_step_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -141,7 +141,10 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // sum to `part[(split*3 + comp)*n_local + i]`; pcl_k_gravity_reduce adds the pieces in a fixed order,
 // so the result does not depend on scheduling.  Bodies in [skip_lo, skip_hi) are left out (the rank's
 // own block, already accumulated while the all-gather was in flight).
-template <int IB, int T, int JT>
+// UM: every j-body has the same mass (BASELINE configs[3]: "equal masses"): the factor m leaves the sum, an
+// interaction is 11 instead of 12 FP32 operations, and padded j-slots sit far away (1e15: their rinv^3 flushes to 0)
+// instead of carrying zero mass.  The caller multiplies G by the common mass.
+template <int IB, int T, int JT, bool UM, int UNR>
 __global__ void __launch_bounds__(T)
 pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__restrict__ pj, uint64_t n_total,
                  float G, float eps2, float *ax, float *ay, float *az, int accumulate, uint64_t skip_lo, uint64_t skip_hi,
@@ -177,8 +180,9 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
         for (int u = 0; u < LP; ++u) {
             const int q = threadIdx.x + u * T;
             const uint64_t j = t * JT + 2 * (uint64_t)q;
-            r0[u] = (q < NP && live_j(j)) ? pj[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[u] = (q < NP && live_j(j + 1)) ? pj[j + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float far = UM ? 1e15f : 0.f;
+            r0[u] = (q < NP && live_j(j)) ? pj[j] : make_float4(far, far, far, 0.f);
+            r1[u] = (q < NP && live_j(j + 1)) ? pj[j + 1] : make_float4(far, far, far, 0.f);
         }
     };
 
@@ -200,7 +204,7 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
     int buf = 0;
     for (uint64_t k = k_begin; k < k_end; ++k, buf ^= 1) {
         if (k + 1 < k_end) fetch(tile_of(k + 1));  // global loads in flight while this tile is consumed
-#pragma unroll 4
+#pragma unroll UNR
         for (int q = 0; q < NP; ++q) {
             const ulonglong2 A = s_a[buf][q], B = s_b[buf][q];
 #pragma unroll
@@ -213,7 +217,7 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
                 upk(r2, lo, hi);
                 f32x2 rinv = pk(pcl_rsqrt_approx(lo), pcl_rsqrt_approx(hi));
                 f32x2 rinv2 = mul2(rinv, rinv);
-                f32x2 sc = mul2(B.y, rinv);
+                f32x2 sc = UM ? rinv : mul2(B.y, rinv);
                 sc = mul2(sc, rinv2);
                 axi[m] = fma2(sc, dx, axi[m]);
                 ayi[m] = fma2(sc, dy, ayi[m]);
@@ -273,10 +277,29 @@ pcl_k_gravity_reduce(const float *__restrict__ part, uint32_t nsplit, uint64_t n
     }
 }
 
+static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local, const float *posm_all,
+                         uint64_t n_total, float G, float eps2, float *ax, float *ay, float *az, int accumulate,
+                         uint64_t j_skip_begin, uint64_t j_skip_end, bool uniform_mass);
+
 extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
                                  const float *posm_all, uint64_t n_total, float G, float eps2, float *ax, float *ay,
                                  float *az, int accumulate, uint64_t j_skip_begin, uint64_t j_skip_end) {
     PCL_ENTER(ctx);
+    return gravity_accel(ctx, stream, posm_local, n_local, posm_all, n_total, G, eps2, ax, ay, az, accumulate, j_skip_begin,
+                         j_skip_end, false);
+}
+
+extern "C" int pcl_gravity_accel_uniform(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local,
+                                         const float *posm_all, uint64_t n_total, float G_times_m, float eps2, float *ax,
+                                         float *ay, float *az, int accumulate, uint64_t j_skip_begin, uint64_t j_skip_end) {
+    PCL_ENTER(ctx);
+    return gravity_accel(ctx, stream, posm_local, n_local, posm_all, n_total, G_times_m, eps2, ax, ay, az, accumulate,
+                         j_skip_begin, j_skip_end, true);
+}
+
+static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local, uint64_t n_local, const float *posm_all,
+                         uint64_t n_total, float G, float eps2, float *ax, float *ay, float *az, int accumulate,
+                         uint64_t j_skip_begin, uint64_t j_skip_end, bool uniform_mass) {
     PCL_REQUIRE(ctx, posm_local && posm_all && ax && ay && az, "null argument");
     PCL_REQUIRE(ctx, pcl_aligned16(posm_local) && pcl_aligned16(posm_all), "posm arrays must be 16-byte aligned");
     PCL_REQUIRE(ctx, eps2 > 0.f, "softening eps2 must be > 0 (the i == j term relies on it)");
@@ -301,11 +324,39 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
     unsigned nsplit = 1;
     {
         const uint64_t itiles = (n_local + 255) / 256, jtiles = (n_total + 511) / 512;
-        // 7 CTAs of 4 warps per SM is what the register budget admits: cut j so that all CTAs fit in ONE
-        // wave (floor, not ceil: a second, mostly empty wave costs more than a slightly emptier first one)
-        uint64_t want = ((uint64_t)ctx->sm_count * 7) / itiles;
-        if (want < 1) want = 1;
+        // 8 CTAs of 4 warps per SM is what the register budget admits (64 registers).  The j range is cut so that
+        // (a) there are several CTAs per resident slot (the kernel is latency-bound below ~8 warps per scheduler:
+        // 0.62 -> 0.75 of the FP32 peak at 256 Ki bodies, profiles/README.md) and (b) the last wave is nearly full.
+        // Every split keeps at least 8 tiles of 512 bodies.
+        static int per_sm = 0;  // resident CTAs per SM of the default kernel (register-limited), asked once
+        if (per_sm == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcl_k_gravity_x2<2, 128, 512, true, 8>, 128, 0) != cudaSuccess || nb < 1) nb = 7;
+            per_sm = nb;
+        }
+        const uint64_t slots = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+        uint64_t hi = jtiles / 8;
+        if (hi > 64) hi = 64;
+        uint64_t want = 1;
+        double best = -1.0;
+        for (uint64_t sp = 1; sp <= hi; ++sp) {
+            const double waves = (double)(itiles * sp) / (double)slots;
+            const double full = (double)(uint64_t)(waves + 0.999999);
+            // fill of the last wave, with a mild preference for about 6 waves (splits cost a partial-sum pass)
+            const double score = waves / full - 0.004 * (waves > 6.0 ? waves - 6.0 : 6.0 - waves);
+            if (score > best) {
+                best = score;
+                want = sp;
+            }
+        }
+        static int force = -1;
+        if (force < 0) {
+            const char *e = getenv("PCL_GRAV_NSPLIT");  // tuning aid
+            force = e ? atoi(e) : 0;
+        }
+        if (force > 0) want = (uint64_t)force;
         if (want > jtiles / 2) want = jtiles / 2;
+        if (want < 1) want = 1;
         if (want > 64) want = 64;
         if (want > 1 && (variant == 0 || variant >= 10)) {
             nsplit = (unsigned)want;
@@ -320,10 +371,15 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
             part = ctx->grav_part;
         }
     }
-#define PCL_GRAV2(IB, T, JT)                                                                                  \
-    pcl_k_gravity_x2<IB, T, JT><<<dim3((unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), nsplit), T, 0, st>>>(  \
+#define PCL_GRAV2U(IB, T, JT, UM, UNR)                                                                        \
+    pcl_k_gravity_x2<IB, T, JT, UM, UNR><<<dim3((unsigned)((n_local + (T) * (IB)-1) / ((T) * (IB))), nsplit), T, 0, st>>>(  \
         (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate, \
         j_skip_begin, j_skip_end, part)
+#define PCL_GRAV2(IB, T, JT)                                     \
+    do {                                                         \
+        if (uniform_mass) PCL_GRAV2U(IB, T, JT, true, 4);        \
+        else PCL_GRAV2U(IB, T, JT, false, 4);                    \
+    } while (0)
     switch (variant) {
         case 1: PCL_GRAV(4, 128); break;
         case 2: PCL_GRAV(2, 128); break;
@@ -338,10 +394,20 @@ extern "C" int pcl_gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *po
         case 13: PCL_GRAV2(2, 128, 1024); break;
         case 14: PCL_GRAV2(2, 64, 256); break;
         case 15: PCL_GRAV2(1, 128, 256); break;
-        default: PCL_GRAV2(2, 128, 512); break;
+        case 16:
+            if (uniform_mass) PCL_GRAV2U(2, 128, 512, true, 8);
+            else PCL_GRAV2U(2, 128, 512, false, 8);
+            break;
+        case 17: PCL_GRAV2(4, 128, 512); break;
+        case 18: PCL_GRAV2(2, 256, 512); break;
+        default:  // 2 i-bodies per thread, 128 threads, 512-body j-tiles, 8 j-pairs unrolled (72 registers)
+            if (uniform_mass) PCL_GRAV2U(2, 128, 512, true, 8);
+            else PCL_GRAV2U(2, 128, 512, false, 8);
+            break;
     }
 #undef PCL_GRAV
 #undef PCL_GRAV2
+#undef PCL_GRAV2U
     PCL_LAUNCHED(ctx);
     if (part) {
         unsigned grid = pcl_stream_grid(ctx, n_local, PCL_BLOCK, 8);

@@ -81,7 +81,7 @@ class GravityExchange:
         self.side = torch.cuda.Stream(device=device)
         self.device = device
 
-    def accelerations(self, ctx, store, posm, n, args):
+    def accelerations(self, ctx, store, posm, n, args, fn="pcl_gravity_accel"):
         import torch
 
         d = _dist()
@@ -91,10 +91,10 @@ class GravityExchange:
         with torch.cuda.stream(self.side):
             d.all_gather_into_tensor(self.all, posm)
         # local block first (overlaps the gather) ...
-        ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0,
+        ctx.call(fn, store.stream(), p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0,
                  C.c_uint64(0), C.c_uint64(0))
         cur.wait_stream(self.side)
         # ... then every other rank's block in ONE launch over the gathered array, own block skipped
         nl = self.n_local
-        ctx.call("pcl_gravity_accel", store.stream(), p(posm), C.c_uint64(n), p(self.all), C.c_uint64(self.world * nl), *args, 1,
+        ctx.call(fn, store.stream(), p(posm), C.c_uint64(n), p(self.all), C.c_uint64(self.world * nl), *args, 1,
                  C.c_uint64(self.rank * nl), C.c_uint64((self.rank + 1) * nl))

@@ -85,6 +85,9 @@ class NewtonianGravityStep(physicl.Step):
             raise RuntimeError("NewtonianGravityStep acts on generic objects; none are present")
         n = g.n
         m = np.ones(n, np.float32) if self.masses is None else np.asarray(self.masses, np.float32).reshape(-1)
+        # equal masses (BASELINE configs[3]): the common mass leaves the pair sum (pcl_gravity_accel_uniform)
+        uniform = bool(m.size) and bool(np.all(m == m[0]))
+        m0 = float(m[0]) if m.size else 1.0
         if m.size != n:
             lo = g.id_base
             m = m[lo:lo + n]
@@ -92,7 +95,7 @@ class NewtonianGravityStep(physicl.Step):
         posm[:, 0], posm[:, 1], posm[:, 2] = g.planes["x"][:n], g.planes["y"][:n], g.planes["z"][:n]
         posm[:, 3] = torch.from_numpy(m).to(st.device)
         acc = torch.zeros((3, n), dtype=torch.float32, device=st.device)
-        self._state = dict(posm=posm, acc=acc, n=n, all=None, store=st)
+        self._state = dict(posm=posm, acc=acc, n=n, all=None, store=st, uniform=uniform, m0=m0)
         if sim.shard:
             from .dist import GravityExchange
 
@@ -108,11 +111,13 @@ class NewtonianGravityStep(physicl.Step):
         n, posm, acc = s["n"], s["posm"], s["acc"]
         ctx, stream = sim.cl_ctx, st.stream()
         p = lambda t: C.c_void_p(t.data_ptr())
-        args = (C.c_float(self.G), C.c_float(self.eps2), p(acc[0]), p(acc[1]), p(acc[2]))
+        fn = "pcl_gravity_accel_uniform" if s["uniform"] else "pcl_gravity_accel"
+        g_eff = self.G * s["m0"] if s["uniform"] else self.G
+        args = (C.c_float(g_eff), C.c_float(self.eps2), p(acc[0]), p(acc[1]), p(acc[2]))
         if "xchg" in s:
-            s["xchg"].accelerations(ctx, st, posm, n, args)
+            s["xchg"].accelerations(ctx, st, posm, n, args, fn)
         else:
-            ctx.call("pcl_gravity_accel", stream, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0, C.c_uint64(0), C.c_uint64(0))
+            ctx.call(fn, stream, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0, C.c_uint64(0), C.c_uint64(0))
         ctx.call("pcl_gravity_kick_drift", stream, C.c_uint64(n), p(posm), p(g.planes["vx"]), p(g.planes["vy"]),
                  p(g.planes["vz"]), p(acc[0]), p(acc[1]), p(acc[2]), C.c_float(float(sim.dt)),
                  p(g.planes["x"]), p(g.planes["y"]), p(g.planes["z"]))

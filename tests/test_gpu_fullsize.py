@@ -1,8 +1,9 @@
-"""BASELINE.json's configurations at FULL size, checked through properties that do not need a CPU
-replay (the oracle takes minutes at these sizes): conservation of photons row by row, independence
-of the result from how timesteps are grouped into launches and from the compaction cadence,
-uniqueness of the surviving ids, binomial/normal bounds on the stochastic counts, closed-form
-kinematics, Newton's third law."""
+"""BASELINE.json's configurations at FULL size.  First through properties that need no CPU replay
+(conservation of photons row by row, independence of the result from how timesteps are grouped into
+launches and from the compaction cadence, uniqueness of the surviving ids, binomial/normal bounds on
+the stochastic counts, closed-form kinematics, Newton's third law); then, at the end of the file,
+against the CPU oracle itself: 16 Mi and 64 Mi photons bit for bit against the binary32 twin, 4096
+sampled bodies of the 256 Ki-body cluster against the float64 definition."""
 import numpy as np
 import pytest
 
@@ -163,3 +164,123 @@ def test_config3_gravity_256k_third_law_and_scaling():
     a_r = -(acc * pos).sum(axis=0) / rr
     plummer = rr / (rr ** 2 + 1.0) ** 1.5  # G M r / (r^2 + a^2)^(3/2), the smooth Plummer field
     assert np.median(np.abs(a_r[sel] / plummer[sel] - 1.0)) < 0.05
+
+
+# ---- BASELINE sizes against the CPU oracle (the binary32 twin steps 16 Mi photons in well under a second per
+# ---- timestep on the box's host cores; the float64 gravity definition is evaluated for a sample of i-bodies) --------
+def _plane_digest(snap, names):
+    """Order-independent 64-bit digests of the planes of a snapshot sorted by id: sum and xor of (bits * odd(id))."""
+    ids = snap["id"].astype(np.uint64)
+    w = ids * np.uint64(0x9E3779B97F4A7C15) | np.uint64(1)
+    out = {}
+    for nm in names:
+        bits = np.ascontiguousarray(snap[nm]).view(np.uint32).astype(np.uint64)
+        out[nm] = (int(np.bitwise_xor.reduce(bits * w)), int((bits * w).sum(dtype=np.uint64)))
+    return out
+
+
+def test_config1_sphere_16m_bit_exact_against_the_oracle_twin():
+    """16 Mi photons, 14 timesteps through every launch form the bulk path uses (8 timesteps in one compacting launch,
+    then 4 + 2 around a compaction boundary: photons start escaping in timestep 11): every tally row and every surviving
+    photon's state equal to the CPU twin's, bit for bit."""
+    import oracle
+
+    n, steps = 16 * 2 ** 20, 14
+    sim, esc, sign = _sphere(n, steps)
+    rows = _rows(sim, 0)
+    host = {k: np.zeros(n, np.float32) for k in ("x", "y", "z", "vx", "vy", "vz")}
+    host["vx"][:] = np.float32(C_LIGHT)
+    for s in range(steps):
+        want = oracle.photon_step_f32(host, 1e-3, 1e-6, C_LIGHT, 0, seed=sim.steps[2]._seed(sim), step=s,
+                                      r2_escape=np.float32(3.0e6 ** 2))
+        assert np.array_equal(rows[s], want), (s, rows[s], want)
+    assert rows[-1, _capi.T_ALIVE] < n  # photons did retire, so compaction moved things
+    assert sim.store.compactions >= 2
+    snap = sim.store.snapshot("photon")
+    live = np.nonzero(~np.isnan(host["x"]))[0]
+    assert np.array_equal(snap["id"], live.astype(np.uint32))
+    twin = {k: host[k][live] for k in host}
+    twin["id"] = live.astype(np.uint32)
+    names = ("x", "y", "z", "vx", "vy", "vz")
+    assert _plane_digest(snap, names) == _plane_digest(twin, names)
+    for k in names:  # and plainly, element by element
+        assert np.array_equal(snap[k].view(np.uint32), twin[k].view(np.uint32)), k
+
+
+def test_config2_wavelength_64m_bit_exact_against_the_oracle_twin():
+    """64 Mi photons with energies from the device sampler, Rayleigh law, 3 timesteps (one fused in-place launch):
+    tally rows and all seven planes equal to the CPU twin's, bit for bit; the sampled bins equal the oracle's."""
+    import oracle
+
+    n, steps = 64 * 2 ** 20, 3
+    sim = phys.Simulation(cl_on=True, seed=2025, exit=lambda s: False)
+    ctx = sim.cl_ctx
+    dev = torch.device("cuda", ctx.device)
+    E_min = float(phys.light.E_from_wavelength(2500e-9))
+    E_max = float(phys.light.E_from_wavelength(200e-9))
+    e, E0, bins = phys.light.planck_sample_device(ctx, n, E_min, E_max, 5778.0, bins=50000, seed=2025, device=dev, want_bins=True)
+    Egrid, _, cdf = phys.light.planck_table(E_min, E_max, 5778.0, 50000)
+    step_e = (Egrid[-1] - Egrid[0]) / (len(Egrid) - 1)
+    m = 2 ** 20  # the sampler against the oracle's linear scan of the reference (light.py:101-104) on the first Mi photons
+    e_o, b_o = oracle.planck_sample(m, 0, 2025, cdf, np.float32(Egrid[0] / E0), np.float32(step_e / E0))
+    assert np.array_equal(bins[:m].cpu().numpy(), b_o)
+    e = torch.nan_to_num(e.contiguous(), nan=0.5)
+    r = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v = torch.zeros((3, n), dtype=torch.float32, device=dev)
+    v[0].fill_(C_LIGHT)
+    sim.add_particles(r, v, E=e)
+    A, nd, dt = 5.1e-31 * (532e-9) ** 4, 2.5e25, 1e-5
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
+    sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+    scat = phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True)
+    sim.add_step(2, scat)
+    sim.add_step(3, phys.light.ScatterSignMeasureStep(None, True))
+    g = sim.device_store().group("photon")
+    g.e0 = E0
+    host = {k: np.zeros(n, np.float32) for k in ("x", "y", "z", "vx", "vy", "vz")}
+    host["vx"][:] = np.float32(C_LIGHT)
+    host["e"] = e.cpu().numpy().copy()
+    k32 = scat.scatter_params(g).k
+    sim.run_steps(steps)
+    rows = _rows(sim, 0)
+    for s in range(steps):
+        want = oracle.photon_step_f32(host, dt, k32, C_LIGHT, oracle.WAVELENGTH, seed=scat._seed(sim), step=s)
+        assert np.array_equal(rows[s], want), (s, rows[s], want)
+    assert 0.03 * n < rows[0, _capi.T_SCATTERED] < 0.12 * n
+    for k in ("x", "y", "z", "vx", "vy", "vz", "e"):
+        assert np.array_equal(g.download(k).view(np.uint32), host[k].view(np.uint32)), k
+
+
+def test_config3_gravity_256k_sampled_bodies_against_the_float64_definition():
+    """4096 randomly chosen i-bodies of the 256 Ki-body Plummer sphere: accelerations from the all-pairs kernel against the
+    float64 definition summed over ALL 262144 j-bodies (a kernel that dropped a j-tile, or a body, would be off by far
+    more than the tolerance).  NEW step: parity unpinned by the reference, the oracle is the definition."""
+    import oracle
+
+    n = 262144
+    rng = np.random.default_rng(7)
+    m_r = rng.uniform(0, 1, n)
+    rad = 1.0 / np.sqrt(np.maximum(m_r ** (-2.0 / 3.0) - 1.0, 1e-12))
+    d = rng.normal(size=(3, n))
+    pos = (rad * d / np.linalg.norm(d, axis=0)).astype(np.float32)
+    sim = phys.Simulation(cl_on=True, exit=lambda s: False)
+    sim.add_particles(pos, np.zeros((3, n)), kind="object")
+    sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+    masses = np.full(n, 1.0 / n, np.float32)
+    sim.add_step(1, phys.newton.NewtonianGravityStep(G=1.0, eps2=1e-4, masses=masses))
+    sim.run_steps(1)
+    g = sim.store.group("object")
+    acc = np.stack([g.download(q) for q in ("vx", "vy", "vz")]).astype(np.float64) / 1e-3  # v = a dt after one step from rest
+    pick = np.sort(rng.choice(n, 4096, replace=False))
+    pos64 = np.ascontiguousarray(pos.astype(np.float64))
+    m64 = masses.astype(np.float64)
+    want = oracle.gravity_pick_f64(pos64, m64, 1.0, 1e-4, pick)
+    got = acc[:, pick]
+    mag = np.linalg.norm(want, axis=0)
+    diff = np.linalg.norm(got - want, axis=0)
+    # float32 accumulation over 262144 terms + rsqrt.approx (2 ulp) + v = a*dt rounding: ~2e-6 of |a_i| for a typical body.
+    # Near the centre the pulls cancel (|a_i| is a small difference of large sums), so the absolute error is measured
+    # against the larger of |a_i| and the cluster's rms acceleration.
+    rms = np.sqrt(np.mean(mag ** 2))
+    worst, med, worst_rel = float((diff / np.maximum(mag, rms)).max()), float(np.median(diff / mag)), float((diff / mag).max())
+    assert worst < 1e-5 and med < 5e-6 and worst_rel < 5e-4, (worst, med, worst_rel)

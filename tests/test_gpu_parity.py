@@ -431,6 +431,31 @@ def test_gravity_matches_float64_definition(ctx, n):
         assert np.abs(f).max() <= 1e-4 * np.abs(got * m32[None]).sum(1).max()
 
 
+@pytest.mark.parametrize("n", [1, 3, 513, 3001])
+def test_gravity_uniform_mass_matches_float64_definition(ctx, n):
+    """pcl_gravity_accel_uniform (equal masses, G*m passed, posm.w ignored), including a ragged skip range and ragged
+    tile ends (padded j-slots must contribute exactly nothing)."""
+    rng = np.random.default_rng(100 + n)
+    pos = rng.normal(size=(3, n))
+    m0, G, eps2 = 0.37, 2.0, 1e-4
+    posm = torch.from_numpy(np.ascontiguousarray(np.vstack([pos, rng.uniform(5, 9, (1, n))]).T, np.float32)).cuda()  # w: junk on purpose
+    acc = torch.zeros((3, n), dtype=torch.float32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    lo, hi = (n // 3, (2 * n) // 3)
+    own = posm[lo:hi].contiguous()
+    if hi > lo:  # own block first, then everything else with the block skipped (the sharded calling sequence)
+        ctx.call("pcl_gravity_accel_uniform", None, p(posm), C.c_uint64(n), p(own), C.c_uint64(hi - lo), C.c_float(G * m0),
+                 C.c_float(eps2), p(acc[0]), p(acc[1]), p(acc[2]), 0, C.c_uint64(0), C.c_uint64(0))
+    ctx.call("pcl_gravity_accel_uniform", None, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), C.c_float(G * m0), C.c_float(eps2),
+             p(acc[0]), p(acc[1]), p(acc[2]), int(hi > lo), C.c_uint64(lo), C.c_uint64(hi))
+    torch.cuda.synchronize()
+    pos32 = np.ascontiguousarray(posm[:, :3].T.cpu().numpy().astype(np.float64))
+    want = oracle.gravity_f64(pos32, np.full(n, m0), G, eps2)
+    got = acc.cpu().numpy().astype(np.float64)
+    scale = np.abs(want).max() if n > 1 else 1.0
+    assert np.abs(got - want).max() <= 1e-5 * scale + 1e-12
+
+
 def test_gravity_split_blocks_equal_whole(ctx):
     """Sharded accumulation (local block, then remote blocks with accumulate=1) equals one pass."""
     n = 2048
