@@ -359,7 +359,8 @@ class Simulation(threading.Thread):
         keep = []
         for kind, g in st.groups.items():
             snap = st.snapshot(kind, live_only=True)
-            if g.host_objs is None:
+            fresh = g.host_objs is None
+            if fresh:
                 from . import light
 
                 cls = light.PhotonObject if kind == "photon" else Object
@@ -367,12 +368,20 @@ class Simulation(threading.Thread):
                 for i in snap["id"]:
                     o = cls.__new__(cls)
                     Object.__init__(o)
+                    o._pcl_origin = (id(st), kind, int(i))  # which bulk particle this object stands for
                     g.host_objs[int(i)] = o
             for j, i in enumerate(snap["id"]):
                 o = g.host_objs[int(i)]
+                v_new = np.array([snap["vx"][j], snap["vy"][j], snap["vz"][j]], np.float64)
+                # Object.dv (physicl/__init__.py:392; written by the scatter step, light.py:325-331: v_new - v_old for a
+                # photon that scattered, zero otherwise): the change of v since the object was last current on the host.
+                # With a host step in the pipeline that is once per timestep, i.e. exactly the reference's value.
+                dv = np.zeros(3) if fresh else v_new - np.asarray(o.v, np.float32).astype(np.float64)  # state is binary32 on the device
+                o.dv = Measurement(dv, "")
+                o.dv.scale, o.dv.units, o.dv.original_units = np.double(1), {"L": 1, "T": -1}, {"m": 1, "s": -1}
                 o.r = Measurement([snap["x"][j], snap["y"][j], snap["z"][j]], "")
                 o.r.scale, o.r.units, o.r.original_units = np.double(1), {"L": 1}, {"m": 1}
-                o.v = Measurement([snap["vx"][j], snap["vy"][j], snap["vz"][j]], "")
+                o.v = Measurement(v_new, "")
                 o.v.scale, o.v.units, o.v.original_units = np.double(1), {"L": 1, "T": -1}, {"m": 1, "s": -1}
                 if "dx" in snap:
                     o.dr = Measurement([snap["dx"][j], snap["dy"][j], snap["dz"][j]], "")

@@ -479,8 +479,14 @@ class TracePathMeasureStep(physicl.MeasureStep):
     Device form: each timestep one kernel scatters r by particle id into that step's slab of a
     trajectory buffer (NaN where the object does not exist any more); ``terminate`` downloads the
     slabs and lays ``data`` out exactly like the reference: first row ``["t", t_0, t_1, ...]``, then per
-    object ``[id_info, (freq,) r_0, r_1, ..., nan, nan, nan, ...]``.  The scatter count comes from the
-    per-photon ``nscat`` plane that every scatter kernel maintains."""
+    object ``[id_info, (freq,) nan, nan, nan, ... , r_k, r_k+1, ..., nan, nan, nan, ...]``: three NaNs for every
+    timestep before the object's first appearance (light.py:477-479; objects may be added while the simulation runs),
+    its positions, and ``[nan, nan, nan] * (columns - positions)`` after them (the reference's own arithmetic, light.py:478,
+    :481).  The scatter count comes from the per-photon ``nscat`` plane that every scatter kernel maintains.
+
+    Identity: like the reference (light.py:450-456) every object gets a trace id the first time it is seen; it is kept
+    in the object's ``__trace_path_id`` attribute, so it survives rebuilds of the device store (a host step, add_obj in
+    the middle of a run).  Bulk particles (``add_particles``) are numbered by their particle id."""
 
     uses_device = True
 
@@ -489,8 +495,13 @@ class TracePathMeasureStep(physicl.MeasureStep):
         self.trace_type = trace_type
         self.id_info_fn = id_info_fn
         self.trace_dv = trace_dv
-        self._slabs = []  # (kind, n_ids, device tensor [3*n_ids], column)
-        self._freq = {}  # kind -> int32 device tensor [n_ids]: latest scatter count per id
+        self.id_counter = 0
+        self.id_dict = {}  # trace id -> id_info string
+        self._start = {}  # trace id -> column of the first appearance
+        self._freq_done = {}  # trace id -> scatter count, for store epochs that are over
+        self._epochs = {}  # (store id, kind) -> dict(tid=int64[n_ids], n_ids, freq=device tensor or None)
+        self._bulk_base = {}  # (store id, kind) -> trace id of local id 0, for groups without Python objects
+        self._slabs = []  # (epoch key, device tensor [3*n_ids], column)
 
     def prepare(self, sim):
         """Called once before the first timestep: the scatter counters must exist before any scatter."""
@@ -499,47 +510,95 @@ class TracePathMeasureStep(physicl.MeasureStep):
             for g in st.groups.values():
                 g.ensure("nscat", fill=0)
 
+    def _epoch(self, sim, st, kind, g, col):
+        """Trace ids of one group of one store (a store lives until the host side changes the object list)."""
+        key = (id(st), kind)
+        ep = self._epochs.get(key)
+        if ep is not None and ep["store"] is st:
+            return key, ep
+        self._close_epochs(keep_store=st)
+        n_ids = g.n
+        g.n0 = n_ids  # ids are local indices of the group as ingested
+        tid = np.empty(n_ids, np.int64)
+        objs = g.host_objs if isinstance(g.host_objs, list) else None
+        cls = PhotonObject if kind == "photon" else physicl.Object
+        if objs is not None:
+            for i, o in enumerate(objs):
+                t = getattr(o, "__trace_path_id", None)
+                origin = getattr(o, "_pcl_origin", None)
+                if t is None and origin is not None and origin[:2] in self._bulk_base:
+                    t = self._bulk_base[origin[:2]] + origin[2]  # a bulk particle that became an object on a pull
+                if t is None:
+                    t = self.id_counter
+                    self.id_counter += 1
+                    self.id_dict[t] = self.id_info_fn(o)
+                    self._start[t] = col
+                setattr(o, "__trace_path_id", t)
+                tid[i] = t
+        else:
+            base = self.id_counter
+            self._bulk_base[key] = base
+            self.id_counter += n_ids
+            info = str(cls)
+            for i in range(n_ids):
+                self.id_dict[base + i] = info
+                self._start[base + i] = col
+            tid[:] = base + np.arange(n_ids)
+        ep = {"store": st, "tid": tid, "n_ids": n_ids, "freq": None}
+        if self.trace_dv:
+            import torch
+
+            ep["freq"] = torch.zeros(max(n_ids, 1), dtype=torch.int32, device=st.device)
+        self._epochs[key] = ep
+        return key, ep
+
+    def _close_epochs(self, keep_store=None):
+        """Fold the scatter counts of finished store epochs into the per-trace-id table."""
+        for key, ep in list(self._epochs.items()):
+            if ep["store"] is keep_store or ep.get("closed"):
+                continue
+            if ep["freq"] is not None:
+                f = ep["freq"].cpu().numpy()[: ep["n_ids"]]
+                for i, t in enumerate(ep["tid"]):
+                    self._freq_done[int(t)] = max(self._freq_done.get(int(t), 0), int(f[i]))
+                ep["freq"] = None
+            ep["closed"] = True
+
     def run(self, sim):
         import torch
 
         st = sim.device_store()
+        col = len(sim.ts) - 1
         for kind, g in st.groups.items():
             st.sync_n(kind)
-            n_ids = g.n0 if hasattr(g, "n0") else g.n
-            if not hasattr(g, "n0"):
-                g.n0 = g.n  # ids are local indices of the group as ingested
-                n_ids = g.n0
+            key, ep = self._epoch(sim, st, kind, g, col)
+            n_ids = ep["n_ids"]
             slab = torch.full((3 * max(n_ids, 1),), float("nan"), dtype=torch.float32, device=st.device)
-            freq = None
-            if self.trace_dv:
-                if kind not in self._freq:
-                    self._freq[kind] = torch.zeros(max(n_ids, 1), dtype=torch.int32, device=st.device)
-                freq = C.c_void_p(self._freq[kind].data_ptr())
+            freq = C.c_void_p(ep["freq"].data_ptr()) if ep["freq"] is not None else None
             soa = g.soa()
             sim.cl_ctx.call("pcl_trace_positions", st.stream(), C.byref(soa), C.c_void_p(slab.data_ptr()), C.c_uint64(n_ids), freq)
-            self._slabs.append((kind, n_ids, slab, len(sim.ts) - 1))
+            self._slabs.append((key, slab, col))
 
     def terminate(self, sim):
-        st = sim.store
         ts = list(sim.ts)
         cols = len(ts)
         dat = [["t"] + copy.deepcopy(ts)]
-        if st is not None:
-            for kind, g in st.groups.items():
-                n_ids = getattr(g, "n0", g.n)
-                steps = [(col, slab.cpu().numpy().reshape(3, -1)) for k, _, slab, col in self._slabs if k == kind]
-                freq = None
-                if self.trace_dv:
-                    freq = self._freq[kind].cpu().numpy()[:n_ids] if kind in self._freq else np.zeros(n_ids, np.int64)
-                cls = PhotonObject if kind == "photon" else physicl.Object
-                for i in range(n_ids):
-                    obj = g.host_objs[i] if g.host_objs is not None and not isinstance(g.host_objs, dict) else None
-                    row = [self.id_info_fn(obj) if obj is not None else str(cls)]
-                    if self.trace_dv:
-                        row.append(int(freq[i]))
-                    pos = [np.array(sl[:, i], np.float64) for _, sl in steps if not np.isnan(sl[0, i])]
-                    row.extend(pos)
-                    row.extend([np.nan, np.nan, np.nan] * (cols - len(pos)))  # light.py:480
-                    dat.append(row)
+        self._close_epochs()
+        pos = {t: [] for t in self.id_dict}  # trace id -> positions in time order
+        for key, slab, col in sorted(self._slabs, key=lambda e: e[2]):
+            ep = self._epochs[key]
+            sl = slab.cpu().numpy().reshape(3, -1)
+            live = np.nonzero(~np.isnan(sl[0, : ep["n_ids"]]))[0]
+            for i in live:
+                pos[int(ep["tid"][i])].append(np.array(sl[:, i], np.float64))
+        for t in range(self.id_counter):
+            row = [self.id_dict[t]]
+            if self.trace_dv:
+                row.append(int(self._freq_done.get(t, 0)))
+            p = pos.get(t, [])
+            row.extend([np.nan, np.nan, np.nan] * self._start.get(t, 0))  # light.py:479
+            row.extend(p)
+            row.extend([np.nan, np.nan, np.nan] * (cols - len(p)))  # light.py:478, :481
+            dat.append(row)
         self.data = dat
         super().terminate(sim)

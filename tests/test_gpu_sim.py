@@ -763,3 +763,79 @@ def test_start_after_run_steps_continues_the_random_stream():
     b.run_steps(11)
     assert a.step_index == b.step_index == 11
     assert np.array_equal(np.array(sa.data)[:, 1:], np.array(sb.data)[:, 1:])
+
+
+def test_trace_path_with_objects_added_while_running():
+    """reference light.py:450-456, :477-481: an object first seen at column b gets 3*b NaNs in front of its positions
+    (and, by the reference's own arithmetic, [nan]*3*(columns - positions) behind them).  Objects are added by a host
+    step in the middle of the run, which rebuilds the device store: trace ids must survive that."""
+
+    class Adder(phys.Step):
+        def run(self, sim):
+            if len(sim.ts) == 3:
+                for q in range(2):
+                    o = phys.Object()
+                    o.r = phys.Measurement([100.0 + q, 0.0, 0.0], "m**1")
+                    o.v = phys.Measurement([0.0, 1.0 + q, 0.0], "m**1 s**-1")
+                    sim.add_obj(o)
+
+    x = phys.Simulation(cl_on=True, exit=lambda s: len(s.ts) >= 6)
+    for q in range(3):
+        o = phys.Object()
+        o.r = phys.Measurement([float(q), 0.0, 0.0], "m**1")
+        o.v = phys.Measurement([1.0, 2.0 * q, -1.0], "m**1 s**-1")
+        x.add_obj(o)
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.5)))
+    x.add_step(1, Adder())
+    x.add_step(2, phys.newton.NewtonianKinematicsStep())
+    tr = phys.light.TracePathMeasureStep(None, id_info_fn=lambda o: "obj")
+    x.add_step(3, tr)
+    x.start()
+    x.join()
+    data = tr.data
+    assert data[0][0] == "t" and len(data[0]) == 7 and len(data) == 1 + 5
+    for q in range(3):  # present from the start: 6 positions, nothing else
+        row = data[1 + q]
+        assert row[0] == "obj" and len(row) == 1 + 6
+        for k in range(6):
+            np.testing.assert_allclose(row[1 + k], [q + 0.5 * (k + 1), 2.0 * q * 0.5 * (k + 1), -0.5 * (k + 1)], rtol=1e-6)
+    for q in range(2):  # added before the third timestep's kinematics: first seen at column 2
+        row = data[4 + q]
+        b, npos = 2, 4
+        assert len(row) == 1 + 3 * b + npos + 3 * (6 - npos)
+        assert all(np.isnan(v) for v in row[1:1 + 3 * b])
+        for k in range(npos):
+            np.testing.assert_allclose(row[1 + 3 * b + k], [100.0 + q, (1.0 + q) * 0.5 * (k + 1), 0.0], rtol=1e-6)
+        assert all(np.isnan(v) for v in row[1 + 3 * b + npos:])
+
+
+def test_pulled_objects_carry_dv():
+    """Object.dv (reference light.py:325-331): v_new - v_old for a photon that scattered in the timestep, zero otherwise.
+    A host step that walks sim.objects every timestep sees exactly that."""
+    seen = []
+
+    class Watch(phys.Step):
+        def run(self, sim):
+            seen.append([(np.asarray(o.v, float).copy(), np.asarray(o.dv, float).copy()) for o in sim.objects])
+
+    x = sim(400, seed=4)
+    x.exit = lambda s: len(s.ts) >= 4
+    x.add_step(0, phys.UpdateTimeStep(lambda s: np.double(0.001)))
+    x.add_step(1, phys.newton.NewtonianKinematicsStep())
+    x.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(0.001), n=np.double(0.001)))
+    x.add_step(3, Watch())
+    x.start()
+    x.join()
+    assert len(seen) == 4 and all(len(s) == 400 for s in seen)
+    c32 = float(np.float32(float(phys.light.c)))
+    prev = [np.array([c32, 0.0, 0.0])] * 400
+    scattered = 0
+    for step in seen:
+        for j, (v, dv) in enumerate(step):
+            np.testing.assert_allclose(dv, v - prev[j], rtol=0, atol=1e-3)
+            if np.any(v != prev[j]):
+                scattered += 1
+            else:
+                assert not np.any(dv)
+        prev = [v for v, _ in step]
+    assert 0.2 * 1600 < scattered < 0.4 * 1600
