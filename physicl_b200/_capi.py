@@ -20,7 +20,7 @@ SCATTER_WAVELENGTH, SCATTER_DELETE = 1, 2
 # thread-level SASS instructions executed per live photon-step by the shipped fused kernels (ncu, profiles/README.md);
 # bench.py turns them into the issue-rate roofline of the photon workloads
 PHOTON_INSTR_PER_STEP = 97.6  # profiles/r2/ncu_full_photon_multi_v2.csv, launch 6: 255.87 M warp instructions / (5 x 16 Mi photon-steps) x 32
-PHOTON_INSTR_PER_STEP_WAVE = 102.0  # static count of the in-place loop (scripts/sass_loop.py); ncu capture pending
+PHOTON_INSTR_PER_STEP_WAVE = 105.1  # profiles/r2/ncu_full_photon_wave_inplace.csv: 1764.2 M warp instructions / (8 x 64 Mi photon-steps) x 32
 GRAVITY_KERNEL = "pcl_k_gravity_x2<2,128,512,UM,8> (2 i-bodies per thread, 512-body j-tiles, packed FP32; UM = equal masses)"
 
 _f32p = C.POINTER(C.c_float)
