@@ -531,9 +531,10 @@ def leg_kinematics(args, rank, world, local, n, id_base, clocks, accel=True):
     peak, peak_src = measured_peaks()
     gbs = bpp * n * args.steps / (ms * 1e-3) / 1e9
     chk = int(sum_rows_over_ranks(np.array([state_checksum(g.planes, n)]), world)[0])
-    traffic = None
-    if accel and n == 64 * 2 ** 20:
-        traffic = 4.777e9  # dram__bytes_read + write of one launch, ncu --set full (profiles/r1_ncu_full_kinematics_step.csv)
+    # dram__bytes_read + write of ONE launch of this kernel by ncu, where a capture at this size exists:
+    # 64 Mi particles: profiles/r1_ncu_full_kinematics_step.csv; 2^30: profiles/r2/ncu_dram_kinematics_1b.csv (38.66 GB read +
+    # 38.60 GB written against 77.31 GB algorithmic: no re-reads)
+    traffic = {64 * 2 ** 20: 4.777e9, 2 ** 30: 77.258e9}.get(n) if accel else None
     out = {"value": float(n) * world * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "gpu_launches": launches,
            "particles_per_gpu": n, "law": "v+=a dt; dr=v dt; r+=dr" if accel else "dr=v dt; r+=dr (reference newton.py:14-16)",
            "state_checksum": chk,
