@@ -761,14 +761,23 @@ def bench_gravity(args, rank, world, local, clocks, steps=None):
         "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gravity_256k", "bodies": n_total, "eps2": 1e-4, "dt": 1e-3, "interactions_per_s": inter / (ms * 1e-3),
-                   "exchange": "none (1 GPU)" if world == 1 else "all-gather of the packed (x,y,z,m) blocks per step over NVLink, overlapped "
-                                                                   "with the local-block tile loop",
+                   "exchange": _gravity_exchange_label(sim, world),
                    "centre_of_mass_after_run": com},
         "e2e": None, "gpu_launches": launches,
         "roofline": {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
                      "peak_source": "FFMA-only micro-kernel measured in this run (pcl_measure_fp32_peak); nominal 148 x 128 x 2 x 1.965 GHz = 74.4",
                      "kernel": _gravity_kernel_name(), "algorithmic_flops": "20 FLOP per pairwise interaction", "per_rank": True},
     }
+
+
+def _gravity_exchange_label(sim, world):
+    if world == 1:
+        return "none (1 GPU)"
+    x = type((sim.steps[1]._state or {}).get("xchg")).__name__
+    if x == "GravityExchangeP2P":
+        return ("GravityExchangeP2P: the kick-drift kernel stores every updated body into all ranks' gathered arrays (peer-mapped "
+                "symmetric memory, NVLink stores), one signal-pad barrier per step, one acceleration launch over local HBM")
+    return "GravityExchange: NCCL all-gather of the packed (x,y,z,m) blocks per step, overlapped with the local-block tile loop"
 
 
 def _gravity_kernel_name():

@@ -230,6 +230,16 @@ int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *po
                            float *vy, float *vz, const float *ax, const float *ay, const float *az,
                            float dt, float *x, float *y, float *z);
 
+/* Sharded form of the kick-drift: besides updating this rank's bodies it PUBLISHES them, storing every packed body into
+ * slot slot0 + i of each of the `world` arrays in peer_bufs[] (device addresses of the ranks' gathered arrays in
+ * peer-mapped / symmetric memory, this rank's own included).  Replaces the per-step all-gather: the transfer rides on the
+ * integration kernel's own stores over NVLink.  The caller double-buffers the gathered arrays by timestep parity and
+ * puts one cross-rank, stream-ordered barrier between this call and the next pcl_gravity_accel. */
+int pcl_gravity_kick_drift_p2p(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx,
+                               float *vy, float *vz, const float *ax, const float *ay, const float *az,
+                               float dt, float *x, float *y, float *z, const uint64_t *peer_bufs,
+                               uint32_t world, uint64_t slot0);
+
 /* ---- host-buffer entry point (the reference's per-step marshalling, __init__.py:602-664) ---- */
 /* One fused photon step over HOST SoA planes: chunks are copied H2D, stepped and copied back D2H
  * on rotating streams so PCIe and the kernel overlap.  Host planes should be pinned

@@ -96,6 +96,7 @@ _PROTOS = {
     "pcl_gravity_accel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
     "pcl_gravity_accel_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]),
     "pcl_gravity_kick_drift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcl_gravity_kick_drift_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64]),
     "pcl_photon_step_host": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64]),
     "pcl_photon_step_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pcl_photon_steps_host_compact": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),

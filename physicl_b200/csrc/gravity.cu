@@ -453,3 +453,65 @@ extern "C" int pcl_gravity_kick_drift(pcl_ctx *ctx, uintptr_t stream, uint64_t n
     PCL_LAUNCHED(ctx);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Sharded gravity without an all-gather call: the kick-drift kernel itself publishes every updated body.  Each
+// rank owns a "gathered" array (world x n_local bodies) in peer-mapped (symmetric) memory; after updating body i
+// the thread stores the packed (x,y,z,m) into slot rank*n_local + i of EVERY rank's array: one 16-byte store
+// per peer, 512 contiguous bytes per warp and peer, travelling over NVLink / NVSwitch while the rest of the grid is
+// still integrating.  The arrays are double-buffered by timestep parity and the ranks meet at one stream-ordered
+// barrier per timestep (the caller's, on the symmetric-memory signal pads), after which the next acceleration
+// pass reads all j-bodies from local HBM in a single launch.
+// ---------------------------------------------------------------------------------------------
+#define PCL_MAX_PEERS 16
+struct pcl_peer_bufs {
+    float4 *p[PCL_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_kick_drift_p2p(uint64_t n, float4 *posm, float *vx, float *vy, float *vz, const float *ax, const float *ay,
+                     const float *az, float dt, float *x, float *y, float *z, pcl_peer_bufs peers, uint32_t world,
+                     uint64_t slot0) {
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; i < n; i += stride) {
+        float4 b = posm[i];
+        float u = vx[i] + ax[i] * dt, v = vy[i] + ay[i] * dt, w = vz[i] + az[i] * dt;
+        b.x = b.x + u * dt;
+        b.y = b.y + v * dt;
+        b.z = b.z + w * dt;
+        vx[i] = u;
+        vy[i] = v;
+        vz[i] = w;
+        posm[i] = b;
+        if (x) {
+            x[i] = b.x;
+            y[i] = b.y;
+            z[i] = b.z;
+        }
+#pragma unroll 1
+        for (uint32_t r = 0; r < world; ++r) peers.p[r][slot0 + i] = b;  // peer-mapped: NVLink stores (own rank: local)
+    }
+}
+
+extern "C" int pcl_gravity_kick_drift_p2p(pcl_ctx *ctx, uintptr_t stream, uint64_t n, float *posm, float *vx, float *vy,
+                                          float *vz, const float *ax, const float *ay, const float *az, float dt,
+                                          float *x, float *y, float *z, const uint64_t *peer_bufs, uint32_t world,
+                                          uint64_t slot0) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, posm && vx && vy && vz && ax && ay && az && peer_bufs, "null argument");
+    PCL_REQUIRE(ctx, pcl_aligned16(posm), "posm must be 16-byte aligned");
+    PCL_REQUIRE(ctx, (x && y && z) || (!x && !y && !z), "x, y, z planes come as a triple or not at all");
+    PCL_REQUIRE(ctx, world >= 1 && world <= PCL_MAX_PEERS, "1 to 16 peers");
+    pcl_peer_bufs peers;
+    memset(&peers, 0, sizeof(peers));
+    for (uint32_t r = 0; r < world; ++r) {
+        PCL_REQUIRE(ctx, peer_bufs[r] != 0 && (peer_bufs[r] & 15u) == 0, "peer arrays must be non-null and 16-byte aligned");
+        peers.p[r] = (float4 *)(uintptr_t)peer_bufs[r];
+    }
+    if (n == 0) return 0;
+    unsigned grid = pcl_stream_grid(ctx, n, PCL_BLOCK, 8);
+    pcl_k_kick_drift_p2p<<<grid, PCL_BLOCK, 0, (cudaStream_t)stream>>>(n, (float4 *)posm, vx, vy, vz, ax, ay, az, dt, x, y, z,
+                                                                        peers, world, slot0);
+    PCL_LAUNCHED(ctx);
+    return 0;
+}

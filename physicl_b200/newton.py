@@ -97,9 +97,9 @@ class NewtonianGravityStep(physicl.Step):
         acc = torch.zeros((3, n), dtype=torch.float32, device=st.device)
         self._state = dict(posm=posm, acc=acc, n=n, all=None, store=st, uniform=uniform, m0=m0)
         if sim.shard:
-            from .dist import GravityExchange
+            from .dist import gravity_exchange
 
-            self._state["xchg"] = GravityExchange(posm, st.device)
+            self._state["xchg"] = gravity_exchange(posm, st.device)
         return self._state
 
     def run(self, sim):
@@ -118,7 +118,10 @@ class NewtonianGravityStep(physicl.Step):
             s["xchg"].accelerations(ctx, st, posm, n, args, fn)
         else:
             ctx.call(fn, stream, p(posm), C.c_uint64(n), p(posm), C.c_uint64(n), *args, 0, C.c_uint64(0), C.c_uint64(0))
-        ctx.call("pcl_gravity_kick_drift", stream, C.c_uint64(n), p(posm), p(g.planes["vx"]), p(g.planes["vy"]),
-                 p(g.planes["vz"]), p(acc[0]), p(acc[1]), p(acc[2]), C.c_float(float(sim.dt)),
-                 p(g.planes["x"]), p(g.planes["y"]), p(g.planes["z"]))
+        if "xchg" in s:
+            s["xchg"].kick_drift(ctx, st, n, posm, g, acc, float(sim.dt))
+        else:
+            ctx.call("pcl_gravity_kick_drift", stream, C.c_uint64(n), p(posm), p(g.planes["vx"]), p(g.planes["vy"]),
+                     p(g.planes["vz"]), p(acc[0]), p(acc[1]), p(acc[2]), C.c_float(float(sim.dt)),
+                     p(g.planes["x"]), p(g.planes["y"]), p(g.planes["z"]))
         sim._mark_device_dirty()

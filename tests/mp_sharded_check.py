@@ -74,18 +74,23 @@ def main():
     ng = 4096
     rng = np.random.default_rng(3)
     pos, vel = rng.normal(size=(3, ng)), rng.normal(0, 0.1, (3, ng))
-    gs = gravity_run(True, ng, 3, local, pos, vel)
-    mine = gs.store.snapshot("object")
-    if rank == 0:
-        g1 = gravity_run(False, ng, 3, local, pos, vel)
-        whole = g1.store.snapshot("object")
+    g1 = gravity_run(False, ng, 5, local, pos, vel)  # every rank computes the unsharded answer for its own block
+    whole = g1.store.snapshot("object")
+    for mode in ("p2p", "nccl"):  # stores from the kick-drift kernel into peer memory / NCCL all-gather
+        os.environ["PCL_GRAVITY_EXCHANGE"] = mode
+        gs = gravity_run(True, ng, 5, local, pos, vel)
+        used = type(gs.steps[1]._state["xchg"]).__name__
+        mine = gs.store.snapshot("object")
         lo = gs.store.group("object").id_base
         m = len(mine["x"])
         err = max(np.abs(whole[nm][lo:lo + m] - mine[nm]).max() for nm in ("x", "y", "z", "vx", "vy", "vz"))
         scale = max(np.abs(whole[nm]).max() for nm in ("vx", "vy", "vz"))
-        gok = err <= 1e-5 * scale
-        print("gravity shard check:", "ok" if gok else "MISMATCH", "max err", err)
-        ok &= gok
+        gok = bool(err <= 1e-5 * scale)
+        worst = torch.tensor([0 if gok else 1], device="cuda")
+        dist.all_reduce(worst)
+        if rank == 0:
+            print("gravity shard check (%s -> %s):" % (mode, used), "ok" if int(worst.item()) == 0 else "MISMATCH", "max err on rank 0", err)
+        ok &= int(worst.item()) == 0
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
