@@ -175,7 +175,8 @@ static void trig_init(void) {
     }
 }
 
-/* sin, cos of (table angle k) + b by the addition theorem, cos b = 1 - b^2/2, sin b = b - b^3/6; mul / fmaf only */
+/* sin, cos of (table angle k) + b by the addition theorem, cos b = 1 - b^2/2, sin b = b - b^3/6; mul / fmaf only:
+ * s = fma(sa, cb, ca*sb); c = fma(ca, cb, -(sa*sb)) */
 void orc_sincos_tab(uint32_t k, float b, float *s, float *c) {
     trig_init();
     const float sa = g_trig[k & 511u][0], ca = g_trig[k & 511u][1];

@@ -113,29 +113,6 @@ pcl_k_gravity(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__r
 // Rounding is IEEE per element (identical to the scalar fmaf/add/mul); only the summation order of
 // the j contributions differs from the scalar kernel.
 // ---------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
 // grid = (i tiles, j splits): when there are few i-bodies per GPU (strong scaling: 32 Ki at 8 GPUs is
 // only 128 i-tiles for 148 SMs) the j range is cut into gridDim.y pieces and each CTA writes a partial
 // sum to `part[(split*3 + comp)*n_local + i]`; pcl_k_gravity_reduce adds the pieces in a fixed order,

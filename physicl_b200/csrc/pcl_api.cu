@@ -60,10 +60,11 @@ extern "C" int pcl_init(int device, pcl_ctx **out) {
     ctx->hbm_bytes = prop.totalGlobalMem;
     snprintf(ctx->name, sizeof(ctx->name), "%.120s", prop.name);
     {  // direction table of the photon kernels: (sin, cos)(2 pi k / 512) in double, rounded once to binary32
-        float2 host[PCL_TRIG_N];
+        float host[2 * PCL_TRIG_N];  // sin table, then cos table
         for (int k = 0; k < PCL_TRIG_N; ++k) {
             const double a = 2.0 * 3.14159265358979323846 * (double)k / (double)PCL_TRIG_N;
-            host[k] = make_float2((float)sin(a), (float)cos(a));
+            host[k] = (float)sin(a);
+            host[PCL_TRIG_N + k] = (float)cos(a);
         }
         cudaError_t e2 = cudaMalloc(&ctx->trig, sizeof(host));
         if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->trig, host, sizeof(host), cudaMemcpyHostToDevice);

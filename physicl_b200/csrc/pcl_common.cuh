@@ -40,7 +40,7 @@ struct pcl_ctx {
     size_t grav_cap;
     pcl_hostpipe *pipe;
     // (sin, cos)(2 pi k / 512): the direction table of the photon kernels (pcl_device.cuh), built at pcl_init
-    float2 *trig;
+    float *trig;
 };
 
 void pcl_set_error(pcl_ctx *ctx, const char *fmt, ...);

@@ -55,25 +55,77 @@ __device__ __forceinline__ uint2 pcl_philox2x32_10(uint32_t c0, uint32_t c1, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// sin / cos of the scattering angles, reproducible bit for bit on a CPU: a 512-entry table of
-// (sin, cos)(2 pi k / 512), rounded from double, and the angle addition theorem for the remainder
+// Packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2 = PTX fma/add/sub/mul.rn.f32x2): one instruction, the same IEEE
+// operation on the two halves of a 64-bit register pair.  Same flops as two scalar instructions, half the issue slots:
+// the photon kernels are bound by instruction issue, so their per-photon arithmetic runs on PAIRS of photons.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sin / cos of the scattering angles, reproducible bit for bit on a CPU: 512-entry tables of
+// sin(2 pi k / 512) and cos(2 pi k / 512), rounded from double, and the angle addition theorem for the remainder
 //   sin(a + b) = sin a cos b + cos a sin b,   cos(a + b) = cos a cos b - sin a sin b,   0 <= b < 2 pi / 256
 // with cos b = 1 - b^2/2 and sin b = b - b^3/6 (truncation < 1.6e-8 and < 8e-11; the table entries carry the
 // usual 6e-8 rounding).  mul / fmaf only, no quadrant logic, no conversions on the slow pipe.
-// The table sits in shared memory (4 KB per CTA); `at` is the BYTE offset of the entry.
+// The tables sit in shared memory (sin: 2 KB, then cos: 2 KB, per CTA); `at` is the BYTE offset of the entry
+// inside either table.  Operation order (the CPU twin repeats it):
+//   b2 = b*b; cb = fma(b2, -1/2, 1); sb = fma(b*b2, -1/6, b); s = fma(sa, cb, ca*sb); c = fma(ca, cb, -(sa*sb))
 // ---------------------------------------------------------------------------------------------
 #define PCL_TRIG_N 512
 #define PCL_TRIG_BYTES (PCL_TRIG_N * 8)
+#define PCL_TRIG_COS (PCL_TRIG_N * 4) /* byte offset of the cos table */
 #define PCL_TWO_PI_256 0x1.921fb6p-6f /* 2 pi / 256 : theta = (k8 + f) * this  */
 #define PCL_PI_256 0x1.921fb6p-7f     /* pi / 256   : phi   = (k8 + f) * this  */
+#define PCL_MSIXTH -0x1.555556p-3f
 
 __device__ __forceinline__ void pcl_sincos_tab(const unsigned char *tab, uint32_t at, float b, float &s, float &c) {
-    const float2 t = *reinterpret_cast<const float2 *>(tab + at);
+    const float sa = *reinterpret_cast<const float *>(tab + at);
+    const float ca = *reinterpret_cast<const float *>(tab + PCL_TRIG_COS + at);
     const float b2 = b * b;
     const float cb = fmaf(b2, -0.5f, 1.0f);
-    const float sb = fmaf(b * b2, -0x1.555556p-3f, b);
-    s = fmaf(t.x, cb, t.y * sb);
-    c = fmaf(t.y, cb, -(t.x * sb));
+    const float sb = fmaf(b * b2, PCL_MSIXTH, b);
+    s = fmaf(sa, cb, ca * sb);
+    c = fmaf(ca, cb, -(sa * sb));
+}
+
+// the same for two photons at once (entries at0 / at1, remainders in the halves of b)
+__device__ __forceinline__ void pcl_sincos_tab2(const unsigned char *tab, uint32_t at0, uint32_t at1, f32x2 b, f32x2 &s, f32x2 &c) {
+    const f32x2 sa = pk(*reinterpret_cast<const float *>(tab + at0), *reinterpret_cast<const float *>(tab + at1));
+    const f32x2 ca = pk(*reinterpret_cast<const float *>(tab + PCL_TRIG_COS + at0), *reinterpret_cast<const float *>(tab + PCL_TRIG_COS + at1));
+    const f32x2 b2 = mul2(b, b);
+    const f32x2 cb = fma2(b2, pk(-0.5f, -0.5f), pk(1.0f, 1.0f));
+    const f32x2 sb = fma2(mul2(b, b2), pk(PCL_MSIXTH, PCL_MSIXTH), b);
+    s = fma2(sa, cb, mul2(ca, sb));
+    // -(sa*sb) as 0 - sa*sb: the packed PTX has no negation, and ptxas is free to contract the explicitly rounded packed
+    // mul + sub into one FFMA2 (it does; scalar mul + sub it leaves alone): written this way the value is
+    // fma(ca, cb, -round(sa*sb)) whether or not it contracts, exactly what the scalar form and the CPU twin compute
+    c = fma2(ca, cb, sub2(pk(0.f, 0.f), mul2(sa, sb)));
 }
 
 // One photon's random numbers for one timestep, in the form the step body consumes them.
@@ -83,33 +135,45 @@ struct pcl_draw3 {
     float bt, bp;     // remainders: theta = entry angle + bt (bt < 2 pi/256), phi = entry angle + bp (bp < pi/256)
 };
 
-// from one Philox2x32 block (w0, w1):  ur = w0[31:8];  theta = 2 pi * w1[31:8] / 2^24;  phi = pi * (w1[7:0] : w0[7:0]) / 2^16
-__device__ __forceinline__ pcl_draw3 pcl_draw_bits(uint32_t w0, uint32_t w1) {
+// from one Philox2x32 block (w0, w1):  ur = w0[31:8];  theta = 2 pi * w1[31:8] / 2^24;  phi = pi * (w1[7:0] : w0[7:0]) / 2^16.
+// RAW form: ur, bt, bp are the integer fields converted to float, NOT yet scaled; the packed step body applies the three
+// power-of-two-exact scalings to two photons per instruction (and folds 2^-24 into 1/k).  pcl_draw_finish scales one draw.
+#define PCL_BT_SCALE (PCL_TWO_PI_256 * 0x1p-16f)
+#define PCL_BP_SCALE (PCL_PI_256 * 0x1p-8f)
+__device__ __forceinline__ pcl_draw3 pcl_draw_bits_raw(uint32_t w0, uint32_t w1) {
     pcl_draw3 d;
-    d.ur = (float)(w0 >> 8) * 0x1p-24f;
-    d.at = (w1 >> 20) & 0xff0u;                                    // k8 = w1[31:24], entry 2*k8, 8 bytes each
-    d.bt = (float)((w1 >> 8) & 0xffffu) * (PCL_TWO_PI_256 * 0x1p-16f);
-    d.ap = (w1 & 0xffu) << 3;                                      // k8 = w1[7:0], entry k8
-    d.bp = (float)(w0 & 0xffu) * (PCL_PI_256 * 0x1p-8f);
+    d.ur = (float)(w0 >> 8);
+    d.at = (w1 >> 21) & 0x7f8u;  // k8 = w1[31:24], entry 2*k8, 4 bytes each
+    d.bt = (float)((w1 >> 8) & 0xffffu);
+    d.ap = (w1 & 0xffu) << 2;  // k8 = w1[7:0], entry k8
+    d.bp = (float)(w0 & 0xffu);
     return d;
 }
+__device__ __forceinline__ pcl_draw3 pcl_draw_finish(pcl_draw3 d) {
+    d.ur = d.ur * 0x1p-24f;
+    d.bt = d.bt * PCL_BT_SCALE;
+    d.bp = d.bp * PCL_BP_SCALE;
+    return d;
+}
+__device__ __forceinline__ pcl_draw3 pcl_draw_bits(uint32_t w0, uint32_t w1) { return pcl_draw_finish(pcl_draw_bits_raw(w0, w1)); }
 
 // from injected uniforms (the reference's host draws rtheta = 2 pi u, rphi = pi u, rand; light.py:285)
 __device__ __forceinline__ pcl_draw3 pcl_draw_floats(float ut, float up, float ur) {
     pcl_draw3 d;
     d.ur = ur;
     const float tt = ut * 256.0f, kt = floorf(tt);
-    d.at = ((uint32_t)(int)kt & 0xffu) << 4;
+    d.at = ((uint32_t)(int)kt & 0xffu) << 3;
     d.bt = (tt - kt) * PCL_TWO_PI_256;
     const float tp = up * 256.0f, kp = floorf(tp);
-    d.ap = ((uint32_t)(int)kp & 0xffu) << 3;
+    d.ap = ((uint32_t)(int)kp & 0xffu) << 2;
     d.bp = (tp - kp) * PCL_PI_256;
     return d;
 }
 
-// copy the table (global, built once per context) into this CTA's shared memory; ends with a CTA barrier
-__device__ __forceinline__ void pcl_trig_to_shared(unsigned char *s_tab, const float2 *g_tab) {
-    for (uint32_t q = threadIdx.x; q < PCL_TRIG_N; q += blockDim.x) reinterpret_cast<float2 *>(s_tab)[q] = g_tab[q];
+// copy the tables (global, built once per context: sin[512] then cos[512]) into this CTA's shared memory; ends with
+// a CTA barrier
+__device__ __forceinline__ void pcl_trig_to_shared(unsigned char *s_tab, const float *g_tab) {
+    for (uint32_t q = threadIdx.x; q < 2 * PCL_TRIG_N; q += blockDim.x) reinterpret_cast<float *>(s_tab)[q] = g_tab[q];
     __syncthreads();
 }
 

@@ -7,6 +7,7 @@ struct StepK {
     float dt;
     float k;          // A*n [* (E0/(h c))^4]: run-time compiled variable-density kernels and diagnostics
     float kinv;       // 1/k, folded in float64 on the host: the collision test is |dr|^2 [e^8] >= (rand/k)^2
+    float kinv24;     // kinv * 2^-24 (exact): multiplies the raw 24-bit integer draw
     float c;
     float r2_escape;  // NaN: no sphere (r2 >= NaN is false)
     uint32_t rk[10];  // Philox2x32 round keys key + r*W (key = fold of seed, high id word, stream)
@@ -15,7 +16,7 @@ struct StepK {
     uint32_t axis[PCL_MAX_PLANES];
     float loc[PCL_MAX_PLANES];
     const float *u_theta, *u_phi, *u_rand;
-    const float2 *trig;  // (sin, cos)(2 pi k / 512), k < 512, device memory owned by the context
+    const float *trig;  // sin(2 pi k / 512), k < 512, then cos(...): device memory owned by the context
     // run-time compiled variable-density kernels only (light.py:295-299), all float64 like the reference:
     double kd;      // the kernel's scalar `A` [* (E0/(h c))^4 with the wavelength law]
     double e0;      // E = e * e0 for user expressions that read E[gid]
@@ -114,6 +115,11 @@ __device__ __forceinline__ bool pcl_scatter_one(bool live, float dx, float dy, f
 __device__ __forceinline__ pcl_draw3 pcl_draw_at(const StepK &K, uint32_t step, uint32_t gid_lo) {
     const uint2 w = pcl_philox2x32_10(gid_lo, step, K.rk);
     return pcl_draw_bits(w.x, w.y);
+}
+// the same draw with its three fields still unscaled (see pcl_draw_bits_raw): for pcl_photon_two<..., RAW = true>
+__device__ __forceinline__ pcl_draw3 pcl_draw_at_raw(const StepK &K, uint32_t step, uint32_t gid_lo) {
+    const uint2 w = pcl_philox2x32_10(gid_lo, step, K.rk);
+    return pcl_draw_bits_raw(w.x, w.y);
 }
 
 // stand-alone tallies (ScatterSignMeasureStep / ScatterMeasureStep kernels): one counter per column
@@ -261,6 +267,116 @@ __device__ __forceinline__ bool pcl_photon_one(const StepK &K, const unsigned ch
     return hit;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two photons, one timestep, with the floating-point work in packed form (one FFMA2 / FMUL2 / FADD2 does the same IEEE
+// operation for photon A and photon B): per pair 36 packed instructions instead of 2 x 36 scalar ones; every half is
+// bit-identical to pcl_photon_one.  Decisions, selects and tallies stay per photon.  Fixed laws only (no VARN).
+// ---------------------------------------------------------------------------------------------
+template <bool PL>
+__device__ __forceinline__ void pcl_tally_photon(const StepK &K, bool live, bool hit, bool absorbed, bool esc, bool on, float xx,
+                                                 float yy, float zz, float dx, float dy, float dz, float vx, float vy, float vz,
+                                                 pcl_tally4 &t) {
+    t.b += hit ? 1u : 0u;
+    t.b += absorbed ? (1u << 8) : 0u;
+    t.b += esc ? (1u << 16) : 0u;
+    t.b += live ? (1u << 24) : 0u;
+    uint32_t m = 1u;
+    m += (vx > 0.f) ? (1u << 8) : 0u;
+    m += (vy > 0.f) ? (1u << 16) : 0u;
+    m += (vz > 0.f) ? (1u << 24) : 0u;
+    t.a += on ? m : 0u;
+    if (PL) {
+#pragma unroll
+        for (int q = 0; q < PCL_MAX_PLANES; ++q) {
+            if ((uint32_t)q < K.nplanes) {
+                const uint32_t ax = K.axis[q];
+                const float r = ax == 0 ? xx : (ax == 1 ? yy : zz);
+                const float dd = ax == 0 ? dx : (ax == 1 ? dy : dz);
+                const float prev = r - dd;  // light.py:386: obj.r[0] - obj.dr[0], evaluated after r += dr
+                const float loc = K.loc[q];
+                const bool cross = on && ((prev <= loc && loc <= r) || (prev >= loc && loc >= r));
+                if (q < 4)
+                    t.p0 += cross ? (1u << (8 * q)) : 0u;
+                else
+                    t.p1 += cross ? (1u << (8 * (q - 4))) : 0u;
+            }
+        }
+    }
+}
+
+template <bool WAVE, bool DEL, bool PL, bool RAW>
+__device__ __forceinline__ void pcl_photon_two(const StepK &K, const unsigned char *tab, float &xA, float &xB, float &yA, float &yB,
+                                               float &zA, float &zB, float &vxA, float &vxB, float &vyA, float &vyB, float &vzA,
+                                               float &vzB, float eA, float eB, const pcl_draw3 &dA, const pcl_draw3 &dB,
+                                               pcl_tally4 &t, bool &hitA, bool &hitB) {
+    const bool liveA = xA == xA, liveB = xB == xB;
+    const f32x2 dte = pk(liveA ? K.dt : 0.f, liveB ? K.dt : 0.f);
+    const f32x2 dx = mul2(pk(vxA, vxB), dte), dy = mul2(pk(vyA, vyB), dte), dz = mul2(pk(vzA, vzB), dte);
+    const f32x2 xx = add2(pk(xA, xB), dx), yy = add2(pk(yA, yB), dy), zz = add2(pk(zA, zB), dz);  // NaN + dx is NaN
+    f32x2 s = mul2(dx, dx);
+    s = fma2(dy, dy, s);
+    s = fma2(dz, dz, s);
+    const float kq = RAW ? K.kinv24 : K.kinv;  // RAW: (U * 2^-24) * kinv == U * (kinv * 2^-24), both scalings exact
+    f32x2 q = mul2(pk(dA.ur, dB.ur), pk(kq, kq));
+    q = mul2(q, q);
+    if (WAVE) {
+        const f32x2 e = pk(eA, eB);
+        const f32x2 e2 = mul2(e, e);
+        const f32x2 e4 = mul2(e2, e2);
+        s = mul2(s, mul2(e4, e4));
+    }
+    float lA, lB, qA, qB;
+    upk(s, lA, lB);
+    upk(q, qA, qB);
+    hitA = liveA && (lA >= qA);
+    hitB = liveB && (lB >= qB);
+    if (!DEL) {
+        f32x2 st, ct, sp, cp;
+        f32x2 bt = pk(dA.bt, dB.bt), bp = pk(dA.bp, dB.bp);
+        if (RAW) {
+            bt = mul2(bt, pk(PCL_BT_SCALE, PCL_BT_SCALE));
+            bp = mul2(bp, pk(PCL_BP_SCALE, PCL_BP_SCALE));
+        }
+        pcl_sincos_tab2(tab, dA.at, dB.at, bt, st, ct);  // theta = 2 pi u
+        pcl_sincos_tab2(tab, dA.ap, dB.ap, bp, sp, cp);  // phi   =   pi u
+        const f32x2 c2 = pk(K.c, K.c);
+        const f32x2 cs = mul2(c2, st);
+        float nA, nB;
+        upk(mul2(cs, cp), nA, nB);
+        vxA = hitA ? nA : vxA;
+        vxB = hitB ? nB : vxB;
+        upk(mul2(cs, sp), nA, nB);
+        vyA = hitA ? nA : vyA;
+        vyB = hitB ? nB : vyB;
+        upk(mul2(c2, ct), nA, nB);
+        vzA = hitA ? nA : vzA;
+        vzB = hitB ? nB : vzB;
+    }
+    f32x2 r2 = mul2(xx, xx);
+    r2 = fma2(yy, yy, r2);
+    r2 = fma2(zz, zz, r2);
+    float r2A, r2B, xxA, xxB, yyA, yyB, zzA, zzB, dxA, dxB, dyA, dyB, dzA, dzB;
+    upk(r2, r2A, r2B);
+    upk(xx, xxA, xxB);
+    upk(yy, yyA, yyB);
+    upk(zz, zzA, zzB);
+    upk(dx, dxA, dxB);
+    upk(dy, dyA, dyB);
+    upk(dz, dzA, dzB);
+    const bool absA = DEL && hitA, absB = DEL && hitB;
+    const bool escA = (r2A >= K.r2_escape) && !absA, escB = (r2B >= K.r2_escape) && !absB;
+    const bool onA = liveA && !(absA || escA), onB = liveB && !(absB || escB);
+    pcl_tally_photon<PL>(K, liveA, hitA, absA, escA, onA, xxA, yyA, zzA, dxA, dyA, dzA, vxA, vyA, vzA, t);
+    pcl_tally_photon<PL>(K, liveB, hitB, absB, escB, onB, xxB, yyB, zzB, dxB, dyB, dzB, vxB, vyB, vzB, t);
+    const float qnan = __int_as_float(0x7fc00000);
+    xA = onA ? xxA : qnan;
+    xB = onB ? xxB : qnan;
+    yA = yyA;
+    yB = yyB;
+    zA = zzA;
+    zB = zzB;
+}
+
 // number of valid slots: the view's n, or the device-resident count when the caller keeps it there
 __device__ __forceinline__ uint64_t pcl_valid_slots(const pcl_soa &p) {
     if (p.n_dev) {
@@ -284,13 +400,26 @@ __device__ __forceinline__ void pcl_step_group4_masked(const pcl_soa &p, const S
     const uint32_t base_lo = (uint32_t)p.id_base;
 #pragma unroll
     for (int l = 0; l < 4; ++l)  // four independent Philox chains: the compiler interleaves them
-        d[l] = INJ ? pcl_draw_floats(pcl_f4(ut4, l), pcl_f4(up4, l), pcl_f4(ur4, l)) : pcl_draw_at(K, K.step, base_lo + pcl_u4(id, l));
+        d[l] = INJ ? pcl_draw_floats(pcl_f4(ut4, l), pcl_f4(up4, l), pcl_f4(ur4, l))
+                   : (VARN ? pcl_draw_at(K, K.step, base_lo + pcl_u4(id, l)) : pcl_draw_at_raw(K, K.step, base_lo + pcl_u4(id, l)));
     pcl_tally4 t = {0u, 0u, 0u, 0u};
+    bool hit[4];
+    if (VARN) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            hit[l] = pcl_photon_one<WAVE, DEL, VARN, PL>(K, tab, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
+                                                         pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), d[l], t);
+    } else {
+#pragma unroll
+        for (int l = 0; l < 4; l += 2)
+            pcl_photon_two<WAVE, DEL, PL, !INJ>(K, tab, pcl_f4(x, l), pcl_f4(x, l + 1), pcl_f4(y, l), pcl_f4(y, l + 1), pcl_f4(z, l),
+                                          pcl_f4(z, l + 1), pcl_f4(vx, l), pcl_f4(vx, l + 1), pcl_f4(vy, l), pcl_f4(vy, l + 1),
+                                          pcl_f4(vz, l), pcl_f4(vz, l + 1), pcl_f4(e, l), pcl_f4(e, l + 1), d[l], d[l + 1], t, hit[l],
+                                          hit[l + 1]);
+    }
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const bool hit = pcl_photon_one<WAVE, DEL, VARN, PL>(K, tab, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                             pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), d[l], t);
-        const bool sc = !DEL && hit;
+        const bool sc = !DEL && hit[l];
         any_scat = any_scat || sc;
         pcl_u4(nsc, l) += sc ? 1u : 0u;
     }

@@ -308,13 +308,18 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
 #pragma unroll
             for (int l = 0; l < 4; ++l)  // four independent Philox chains: the compiler interleaves them
                 dr[l] = INJ ? pcl_draw_floats(pcl_f4(ut4, l), pcl_f4(up4, l), pcl_f4(ur4, l))
-                            : pcl_draw_at(K, K.step + st, base_lo + pcl_u4(id, l));
+                            : pcl_draw_at_raw(K, K.step + st, base_lo + pcl_u4(id, l));
             pcl_tally4 t = {0u, 0u, 0u, 0u};
+            bool hit[4];
+#pragma unroll
+            for (int l = 0; l < 4; l += 2)  // photons (0,1) and (2,3) as pairs: packed FP32
+                pcl_photon_two<WAVE, DEL, PL, !INJ>(K, s_tab, pcl_f4(x, l), pcl_f4(x, l + 1), pcl_f4(y, l), pcl_f4(y, l + 1), pcl_f4(z, l),
+                                              pcl_f4(z, l + 1), pcl_f4(vx, l), pcl_f4(vx, l + 1), pcl_f4(vy, l), pcl_f4(vy, l + 1),
+                                              pcl_f4(vz, l), pcl_f4(vz, l + 1), pcl_f4(e, l), pcl_f4(e, l + 1), dr[l], dr[l + 1], t,
+                                              hit[l], hit[l + 1]);
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                const bool hit = pcl_photon_one<WAVE, DEL, false, PL>(K, s_tab, pcl_f4(x, l), pcl_f4(y, l), pcl_f4(z, l), pcl_f4(vx, l),
-                                                                      pcl_f4(vy, l), pcl_f4(vz, l), pcl_f4(e, l), dr[l], t);
-                const bool sc = !DEL && hit;
+                const bool sc = !DEL && hit[l];
                 any_scat = any_scat || sc;
                 pcl_u4(nsc, l) += sc ? 1u : 0u;
             }
@@ -565,6 +570,7 @@ int pcl_fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *s
         } else {
             K.kinv = nanf("");
         }
+        K.kinv24 = ldexpf(K.kinv, -24);
     }
     K.r2_escape = escape_r2 > 0.f ? escape_r2 : nanf("");
     if (rng) {
