@@ -427,7 +427,7 @@ class Simulation(threading.Thread):
         self.ts = []
         self.running = True  # step_index is NOT reset: it is the Philox step counter and must never repeat
         try:
-            if self.cl_on:  # the simulation thread is a new host thread: its current CUDA device is 0 until told otherwise
+            if self.cl_on and self.cl_ctx is not None:  # a new host thread: its current CUDA device is 0 until told otherwise
                 import torch
 
                 torch.cuda.set_device(self.device)

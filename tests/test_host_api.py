@@ -421,3 +421,101 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.split() == [str(len(names)), "1"]
+
+
+# ---- the chunked main loop (Simulation._run_chunked) against a scripted device -----------------------------------------
+class _ScriptedStore:
+    """Stands in for DeviceParticleStore: tally rows of a population that loses a fixed share per timestep."""
+
+    def __init__(self, n):
+        self.n0 = n
+        self.alive = n
+        self.rows = []
+        self.restored = 0
+
+    @property
+    def current_row(self):
+        return len(self.rows) - 1
+
+    def read_row(self, r):
+        return self.rows[r]
+
+    def checkpoint(self, kind):
+        return (self.alive, len(self.rows))
+
+    def restore(self, kind, ck):
+        self.alive = ck[0]  # rows of the discarded timesteps stay in the table, as on the device
+        self.restored += 1
+
+
+class _ScriptedFused(phys.Step):
+    uses_device = True
+    tallies_every_timestep = True
+
+    def __init__(self, store, chunk):
+        self.store, self.chunk, self.calls = store, chunk, []
+
+    def can_run_many(self, sim):
+        return True
+
+    def chunk_steps(self, sim):
+        return self.chunk
+
+    def checkpoint(self):
+        return None
+
+    def rollback(self, ck):
+        pass
+
+    def run_many(self, sim, k, dt, ts):
+        self.calls.append(k)
+        for _ in range(k):
+            self.store.alive = (self.store.alive * 9) // 10
+            row = np.zeros(16, np.int64)
+            row[0] = self.store.alive
+            self.store.rows.append(row)
+        sim._mark_device_dirty()
+
+
+def _scripted_sim(exit_fn, chunk, n=1000, dt_fn=None):
+    sim = phys.Simulation(cl_on=False, exit=exit_fn)
+    st = _ScriptedStore(n)
+    fused = _ScriptedFused(st, chunk)
+    upd = phys.UpdateTimeStep(dt_fn or (lambda s: np.double(0.5)))
+    sim.cl_on = True  # only so that _bulk_plan accepts the pair; no context is ever touched
+    sim._plan = lambda: [upd, fused]
+    sim.device_store = lambda: st
+    sim.store = st
+    sim._device_live_count = lambda: st.alive
+    sim._device_dirty = True  # the scripted device is the authority for len(sim.objects)
+    sim.run()
+    if sim.error:
+        raise sim.error
+    return sim, st, fused
+
+
+@pytest.mark.parametrize("chunk", [1, 4, 64])
+def test_chunked_loop_time_predicate_looks_ahead(chunk):
+    """exit on t: evaluated on the host after every UpdateTimeStep of the chunk; exactly 7 timesteps run, no roll-back."""
+    sim, st, fused = _scripted_sim(lambda s: s.t >= 3.5, chunk)
+    assert len(sim.ts) == 7 and float(sim.t) == 3.5 and sim.step_index == 7 and len(st.rows) == 7
+    assert st.restored == 0 and sum(fused.calls) == 7 and max(fused.calls) <= chunk
+
+
+@pytest.mark.parametrize("chunk", [1, 4, 64])
+def test_chunked_loop_particle_predicate_rolls_back(chunk):
+    """exit on len(objects): checked against the tally row of every timestep of the chunk; the loop ends after the FIRST
+    timestep at which it holds (1000 * 0.9^k <= 500 first at k = 7), whatever the chunk size."""
+    sim, st, fused = _scripted_sim(lambda s: len(s.objects) <= 500, chunk)
+    assert len(sim.ts) == 7 and sim.step_index == 7 and st.alive == 477
+    assert float(sim.t) == 3.5
+    assert st.restored == (0 if chunk == 1 else 1)  # chunk 4: the second chunk (timesteps 5-8) overshoots by one; 64: by 57
+
+
+def test_chunked_loop_mixed_predicate_and_changing_dt():
+    """A predicate that starts looking at the particles only once t is large enough, and a dt that changes."""
+    dt_fn = lambda s: np.double(0.25 if len(s.ts) < 3 else 0.5)  # noqa: E731
+    sim, st, fused = _scripted_sim(lambda s: s.t >= 1.0 and len(s.objects) <= 600, 16, dt_fn=dt_fn)
+    ref, st1, _ = _scripted_sim(lambda s: s.t >= 1.0 and len(s.objects) <= 600, 1, dt_fn=dt_fn)
+    assert [float(t) for t in sim.ts] == [float(t) for t in ref.ts] and st.alive == st1.alive and sim.step_index == ref.step_index
+    assert st.alive <= 600 and len(sim.ts) == 5
