@@ -210,7 +210,9 @@ def sum_rows_over_ranks(rows, world):
 class Gate:
     """Device-side gate in front of a timed region (pcl_stream_gate): the host queues event, launches, event behind
     a one-thread kernel that spins on a word of pinned host memory, then opens it.  The two events therefore bracket
-    GPU work only; host launch latency (Python, ctypes, other ranks' threads) is outside the bracket."""
+    GPU work only; host launch latency (Python, ctypes, other ranks' threads) is outside the bracket.
+    Everything queued behind a closed gate must have run once before (the warm-up does that): the first launch of a
+    kernel loads its module, and module loading waits for running kernels, i.e. for the gate's time-out."""
 
     def __init__(self, ctx):
         import torch
@@ -448,20 +450,24 @@ def run_threaded(sim, steps):
     sim.join()
 
 
-def photon_roofline(live, scat, ms, wave, kernel):
+def photon_roofline(live, scat, ms, wave, kernel, steps_per_launch):
     """The fused photon kernel is bound by instruction issue, not by DRAM (ncu: profiles/README.md).  `achieved` is
     the warp-instruction issue rate implied by the measured instructions per photon-step of the shipped build."""
     from physicl_b200 import _capi
 
     peak, peak_src = measured_peaks()
-    ipp = _capi.PHOTON_INSTR_PER_STEP_WAVE if wave else _capi.PHOTON_INSTR_PER_STEP
+    loop, launch = ((_capi.PHOTON_INSTR_LOOP_WAVE, _capi.PHOTON_INSTR_LAUNCH_WAVE) if wave
+                    else (_capi.PHOTON_INSTR_LOOP, _capi.PHOTON_INSTR_LAUNCH))
+    ipp = loop + launch / max(steps_per_launch, 1.0)
     alg = ((40.0 if wave else 36.0) * live + 12.0 * scat) / (ms * 1e-3) / 1e9
     rate = live / (ms * 1e-3)
     issued = rate * ipp / 32.0
     return {"bound": "issue", "achieved": issued / 1e9, "peak": ISSUE_PEAK / 1e9, "unit": "G warp-instructions/s",
             "frac": issued / ISSUE_PEAK, "traffic": None, "kernel": kernel, "per_rank": True,
             "instructions_per_photon_step": ipp,
-            "instructions_source": "ncu --set full of the shipped kernel, smsp__inst_executed / live photon-steps (profiles/README.md)",
+            "instructions_source": "ncu --set full of the shipped kernel (profiles/README.md): %.1f per photon-step in the timestep loop + %.1f "
+                                   "per photon and launch (load, write-back / compaction) / %.2f timesteps per launch; photons that retire "
+                                   "inside a launch still occupy their lanes, so the true issue rate is a little higher" % (loop, launch, steps_per_launch),
             "hbm_equivalent_gbs": alg, "hbm_equivalent_frac": alg / peak,
             "hbm_equivalent_note": "(%d + 12 f) B per live photon-step (SURVEY.md 8d: one state round trip per timestep) / time / %s; "
                                    "above 1.0 means the fused kernel beats a perfect one-round-trip-per-step streaming kernel; the state "
@@ -500,7 +506,8 @@ def leg_photon(args, rank, world, local, n, id_base, clocks, prime=True, strong=
            "live_fraction_mean": live / (float(n) * args.steps), "scattered_fraction": scat / max(live, 1.0),
            "escaped_in_window": int(rows_all[:, _capi.T_ESCAPED].sum()),
            "tally_checksum": checksum_hex(rows_all),
-           "roofline": photon_roofline(live, scat, ms, False, "pcl_k_photon_multi<0,0,0,0,1> (m <= 8 timesteps per launch, survivors compacted)")}
+           "roofline": photon_roofline(live, scat, ms, False, "pcl_k_photon_multi<0,0,0,0,1> (m <= 8 timesteps per launch, survivors compacted)",
+                                       args.steps / max(launches, 1))}
     return out, rows_all, ms
 
 
@@ -839,7 +846,8 @@ def bench_wavelength(args, rank, world, local, clocks):
                    "planck_sampling_ms": sample_ms, "planck_sampling_gphotons_per_s": n / sample_ms / 1e6,
                    "scattered_fraction": scat / max(live, 1), "l2": "state 1.75 GiB per GPU > L2"},
         "e2e": None, "gpu_launches": launches,
-        "roofline": photon_roofline(live, scat, ms, True, "pcl_k_photon_multi<1,0,0,0,0> (8 timesteps per launch, in place)"),
+        "roofline": photon_roofline(live, scat, ms, True, "pcl_k_photon_multi<1,0,0,0,0> (8 timesteps per launch, in place)",
+                                    args.steps / max(launches, 1)),
         "tally_checksum": checksum_hex(rows_all),
     }
 

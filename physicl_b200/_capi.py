@@ -17,10 +17,14 @@ TALLY_COLS = 16
 T_ALIVE, T_XP, T_YP, T_ZP, T_SCATTERED, T_ABSORBED, T_ESCAPED, T_LIVE_IN, T_PLANE0 = range(9)
 SCATTER_WAVELENGTH, SCATTER_DELETE = 1, 2
 
-# thread-level SASS instructions executed per live photon-step by the shipped fused kernels (ncu, profiles/README.md);
-# bench.py turns them into the issue-rate roofline of the photon workloads
-PHOTON_INSTR_PER_STEP = 97.6  # profiles/r2/ncu_full_photon_multi_v2.csv, launch 6: 255.87 M warp instructions / (5 x 16 Mi photon-steps) x 32
-PHOTON_INSTR_PER_STEP_WAVE = 105.1  # profiles/r2/ncu_full_photon_wave_inplace.csv: 1764.2 M warp instructions / (8 x 64 Mi photon-steps) x 32
+# Thread-level SASS instructions of the shipped fused photon kernels, from ncu (profiles/r2/ncu_full_photon_multi_v3.csv,
+# ncu_full_photon_wave_inplace_v3.csv; static loop counts by scripts/sass_loop.py agree): per photon-step inside the timestep
+# loop, and per photon and LAUNCH for the load + write-back / compaction phase.  bench.py turns them into the issue-rate
+# roofline of the photon workloads: instructions per photon-step = LOOP + LAUNCH / (timesteps per launch).
+PHOTON_INSTR_LOOP = 88.7        # compacting launches of 3 and 4 timesteps: (226.90 M - 180.37 M) warp instructions x 32 / 16 Mi photons
+PHOTON_INSTR_LAUNCH = 77.8      # 180.37 M x 32 / 16 Mi - 3 x 88.7
+PHOTON_INSTR_LOOP_WAVE = 86.2   # wavelength law, in place: static count of the loop (345 per four photons)
+PHOTON_INSTR_LAUNCH_WAVE = 39.6  # 1529.4 M x 32 / (8 x 64 Mi) = 91.15 per photon-step at 8 timesteps per launch
 GRAVITY_KERNEL = "pcl_k_gravity_x2<2,128,512,UM,8> (2 i-bodies per thread, 512-body j-tiles, packed FP32; UM = equal masses)"
 
 _f32p = C.POINTER(C.c_float)

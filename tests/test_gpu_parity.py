@@ -727,3 +727,32 @@ def test_empty_and_tiny_inputs_through_every_bulk_entry_point(ctx):
         rows = np.array([st.read_row(first + i) for i in range(3)])
         assert np.all(rows[:, _capi.T_LIVE_IN] == n)
         mod.close()
+
+
+def test_stream_gate_holds_the_stream_until_opened(ctx):
+    """pcl_stream_gate: work queued behind the gate does not start before the host writes the flag (and does start after)."""
+    import time
+
+    flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+    x = torch.zeros(1 << 20, device="cuda")
+    x.add_(1.0)  # first use loads the kernel's module, which waits for running kernels: not behind a closed gate
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ctx.call("pcl_stream_gate", stream, C.c_void_p(flag.data_ptr()), C.c_uint32(200))  # first use of the gate kernel itself
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ctx.call("pcl_stream_gate", stream, C.c_void_p(flag.data_ptr()), C.c_uint32(5000))
+    x.add_(1.0)
+    ev = torch.cuda.Event()
+    ev.record()
+    time.sleep(0.05)
+    assert not ev.query()  # still behind the gate
+    flag[0] = 1
+    ev.synchronize()
+    assert time.time() - t0 < 2.0  # opened by the flag, not by the 5 s timeout
+    assert float(x[0].item()) == 2.0
+    # a gate nobody opens gives up after its timeout instead of hanging the GPU
+    flag[0] = 0
+    t0 = time.time()
+    ctx.call("pcl_stream_gate", stream, C.c_void_p(flag.data_ptr()), C.c_uint32(200))
+    torch.cuda.synchronize()
+    assert 0.15 < time.time() - t0 < 2.0
