@@ -630,7 +630,15 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         PCL_LAUNCHED(ctx);
         return 0;
     }
-    if (nsteps > 1) {  // several timesteps per HBM round trip, in place
+    static int single_multi = -1;
+    if (single_multi < 0) {
+        // Single timesteps go through the multi-step kernel too (nsteps = 1): since the arithmetic of round 2 it is the
+        // fastest form at 16 Mi live photons (135 us; TMA-staged kernel 146 us, register-load kernel 143 us).
+        // PCL_PHOTON_SINGLE_MULTI=0 restores the dedicated single-step kernels (PCL_PHOTON_TMA picks between them).
+        const char *e = getenv("PCL_PHOTON_SINGLE_MULTI");
+        single_multi = e ? atoi(e) : 1;
+    }
+    if (nsteps > 1 || (single_multi && aligned && !INJ)) {  // several timesteps per HBM round trip, in place
         PCL_REQUIRE(ctx, aligned, "multi-step launches need 16-byte aligned planes");
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
         pcl_k_photon_multi<WAVE, DEL, INJ, PL, false><<<grid, PCL_BLOCK, 0, st>>>(p, p, K, row, nullptr, nsteps);
