@@ -698,6 +698,52 @@ def test_compacting_host_step_equals_resident_steps(ctx, pinned, monkeypatch):
         assert u.same_bits(host[nm].numpy()[:n_live][order], snap[nm]), nm
 
 
+@pytest.mark.parametrize("m", [1, 3, 8])
+def test_multi_timestep_host_round_trips_equal_resident_steps(ctx, m):
+    """pcl_photon_steps_host_compact: m timesteps per host round trip (one fused launch per chunk).  Every tally row
+    and the surviving photons (by id) equal the device-resident path advanced one timestep at a time; n = 0 is a no-op."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    n, steps = 300_011, 9
+    r, v = u.beam_photons(n)
+    st, g = u.make_store(ctx, r, v, id_base=5_000_000)
+    host = {nm: torch.from_numpy(g.download(nm).copy()).pin_memory() for nm in u.PLANE_NAMES}
+    host["id"] = torch.arange(n, dtype=torch.int32).pin_memory()
+    dt, k, c, r2 = 1e-3, 1e-6, u.C_LIGHT, 1.0e6 ** 2
+    want = [u.photon_step(ctx, st, g, dt, k, c, 0, seed=4, step=s, r2_escape=r2, planes=[(0, 7.0e5)]) for s in range(steps)]
+    sp = _capi.ScatterParams(k=k, c=c, mode=0)
+    pl = _capi.make_planes([(0, 7.0e5)])
+    rows = np.zeros((8, _capi.TALLY_COLS), np.int64)
+    n_out = C.c_uint64(0)
+    n_live, s = n, 0
+    while s < steps:
+        run = min(m, steps - s)
+        soa = _capi.Soa()
+        soa.n, soa.id_base = n_live, 5_000_000
+        for nm, t in host.items():
+            setattr(soa, nm, t.data_ptr())
+        rg = _capi.Rng(seed=4, step=s)
+        ctx.call("pcl_photon_steps_host_compact", C.byref(soa), C.c_float(dt), C.byref(sp), C.byref(rg), C.c_float(r2),
+                 C.byref(pl), rows.ctypes.data_as(C.c_void_p), C.c_uint64(32_768), C.c_uint32(run), C.byref(n_out))
+        for q in range(run):
+            assert np.array_equal(rows[q], want[s + q]), (s + q, rows[q], want[s + q])
+        n_live = int(n_out.value)
+        assert n_live == int(want[s + run - 1][_capi.T_ALIVE])
+        s += run
+    assert 0 < n_live < n
+    snap = st.snapshot("photon")
+    ids = host["id"].numpy()[:n_live].view(np.uint32)
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], snap["id"])
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(host[nm].numpy()[:n_live][order], snap[nm]), nm
+    soa.n = 0
+    ctx.call("pcl_photon_steps_host_compact", C.byref(soa), C.c_float(dt), C.byref(sp), C.byref(rg), C.c_float(r2),
+             C.byref(pl), rows.ctypes.data_as(C.c_void_p), C.c_uint64(32_768), C.c_uint32(m), C.byref(n_out))
+    assert n_out.value == 0 and not rows[:m].any()
+
+
 def test_empty_and_tiny_inputs_through_every_bulk_entry_point(ctx):
     """n = 0 is a no-op everywhere (the reference's loops simply do not execute); rows stay zero."""
     from physicl_b200 import _capi, jit
