@@ -96,13 +96,6 @@ class Object:
             setattr(self, attr, val)
 
 
-class _Probe:
-    """Records whether an exit predicate looked at device-side state (particles, measure-step rows) while it was
-    evaluated: predicates that only read ``t`` / ``dt`` / ``ts`` can be evaluated ahead of the device."""
-
-    touched = False
-
-
 class _ObjectList(list):
     """``sim.objects``: a list that knows when the device store is the authority.
 
@@ -146,7 +139,7 @@ class _ObjectList(list):
 
     def __len__(self):
         sim = self._sim
-        _Probe.touched = True
+        sim._probe_touched = True  # an exit predicate that gets here looks at the particles (Simulation._run_chunked)
         if sim._len_override is not None:  # replay of an exit predicate against the tally row of an earlier timestep
             return sim._len_override
         if sim._device_dirty and sim.store is not None:
@@ -160,12 +153,12 @@ class _ObjectList(list):
         return n
 
     def __iter__(self):
-        _Probe.touched = True
+        self._sim._probe_touched = True
         self._sim._pull_objects()
         return super().__iter__()
 
     def __getitem__(self, i):
-        _Probe.touched = True
+        self._sim._probe_touched = True
         self._sim._pull_objects()
         return super().__getitem__(i)
 
@@ -206,6 +199,7 @@ class Simulation(threading.Thread):
         self._device_dirty = False
         self._pending = None  # bulk particles registered with add_particles()
         self._len_override = None
+        self._probe_touched = False  # set by _ObjectList accessors: did the exit predicate look at the particles?
         self.objects = _ObjectList(self)
         self.steps = {}
         self._state_lock = threading.Lock()
@@ -474,8 +468,8 @@ class Simulation(threading.Thread):
             if dts[-1] != dts[0]:
                 break
             if probe_exit and len(dts) < k:
-                _Probe.touched = False
-                if self.exit(self) or _Probe.touched:
+                self._probe_touched = False
+                if self.exit(self) or self._probe_touched:
                     break
         if dts[-1] != dts[0]:  # dt changed inside the chunk: these timesteps go one by one
             for dt_i, t_i in zip(dts, ts):
@@ -498,10 +492,10 @@ class Simulation(threading.Thread):
         before it and re-run up to the firing timestep (the draws are a pure function of particle id and step index,
         so the re-run reproduces those timesteps bit for bit)."""
         while True:
-            _Probe.touched = False
+            self._probe_touched = False
             if self.exit(self):
                 return
-            looks_at_particles = _Probe.touched
+            looks_at_particles = self._probe_touched
             kmax = max(1, min(fused.chunk_steps(self), 256))
             with self._state_lock:
                 if not looks_at_particles:
