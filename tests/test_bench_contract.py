@@ -51,3 +51,38 @@ def test_archived_round1_line_carries_the_contract_keys():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+
+
+def test_archived_round2_lines_carry_the_contract_keys_and_agree_across_n():
+    """The default line as the B200 box printed it at N = 1, 2, 4, 8 (profiles/bench_r2): every key the driver reads, a
+    roofline for each leg and each sub-result, and the SAME tally checksum at every N."""
+    lines = {}
+    for n in (1, 2, 4, 8):
+        with open(os.path.join(REPO, "profiles", "bench_r2", "sweep_1b_n%d.json" % n)) as f:
+            lines[n] = json.loads(f.readline())
+    sys.path.insert(0, REPO)
+    import bench
+
+    for n, d in lines.items():
+        assert BASE_KEYS | {"roofline", "roofline_photon", "clocks", "tally_checksum", "sub", "detail"} <= set(d), n
+        assert d["config"] == bench.SWEEP_CONFIG and d["n_gpus"] == n and d["scaling"] == "strong" and d["dtype"] == "f32"
+        assert d["vs_baseline"] is None and d["higher_is_better"] is True and d["gpu_launches"] > 0
+        rf = d["roofline"]
+        assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12 and 0.9 < rf["frac"] < 1.0
+        rp = d["roofline_photon"]
+        assert rp["bound"] == "issue" and abs(rp["frac"] - rp["achieved"] / rp["peak"]) < 1e-9 and rp["hbm_equivalent_frac"] > 1.0
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and not d["clocks"]["reasons"]
+        e = d["e2e"]
+        assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+        assert e["one_timestep_per_round_trip"]["value"] < e["value"]
+        g = d["sub"]["gravity_256k"]
+        assert g["roofline"]["bound"] == "fp32" and g["roofline"]["frac"] > 0.70
+    assert len({d["tally_checksum"] for d in lines.values()}) == 1
+    assert lines[8]["value"] > 7.0 * lines[1]["value"]  # the north star's >= 7x at 8 GPUs on the 1 B-particle sweep
+    one = lines[1]
+    assert {"value", "unit", "cores", "kind", "sample", "reference_e2e"} <= set(one["cpu_baseline"])
+    assert one["cpu_baseline"]["reference_e2e"]["kind"] == "reference"
+    assert one["roofline"]["traffic"] and abs(one["roofline"]["traffic"] / (72.0 * 2 ** 30) - 1.0) < 0.01
+    for name in ("photon_sphere_16m", "kinematics_64m", "wavelength_64m", "gravity_256k"):
+        assert {"value", "roofline", "config"} <= set(one["sub"][name]), name
+    assert one["sub"]["kinematics_64m"]["roofline"]["frac"] >= 0.70  # north star: >= 70 % of HBM on the kinematic step
