@@ -27,7 +27,8 @@ timestep / all timesteps in registers), wavelength_64m (configs[2]), gravity_256
              checksum of the kinematics state: identical at N = 1, 2, 4, 8 (results do not depend on sharding)
   cpu_baseline / --impl reference
              the same two legs in float64 on the host cores (oracle/c/oracle.c, C + OpenMP; kind "port") on a
-             bounded sample, plus the UNMODIFIED reference end to end (oracle/_ref + oracle/fake_pyopencl)
+             bounded sample, plus the UNMODIFIED reference end to end and its own generated kernel text on
+             pre-marshalled arrays (oracle/_ref + oracle/fake_pyopencl)
 """
 from __future__ import annotations
 
@@ -329,6 +330,31 @@ def reference_python(n=10000, steps=10, timeout=240):
         return {"unavailable": repr(e)}
 
 
+def reference_kernels(n=1_000_000, reps=10, timeout=240):
+    """the reference's own GENERATED kernel text (light_scatter_step_sphere) compiled by
+    gcc with an OpenMP work-item loop, on pre-marshalled float64 arrays, + the kinematics law as NumPy array arithmetic."""
+    try:
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_reference.py"), "--kernels", str(n), "--steps", str(reps)],
+                             capture_output=True, text=True, timeout=timeout, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if not line:
+            return {"unavailable": (out.stderr or out.stdout)[-300:]}
+        d = json.loads(line[-1])
+        if "unavailable" in d:
+            return d
+        return {"value": d["particle_steps_per_s"], "unit": "particle-steps/s", "cores": len(os.sched_getaffinity(0)), "kind": "reference",
+                "scatter_kernel_particles_per_s": d["scatter_kernel_particles_per_s"],
+                "kinematics_numpy_particles_per_s": d["kinematics_numpy_particles_per_s"],
+                "sample": "the kernel text the reference generates for ScatterIsotropicStep (physicl/light.py:303-315 through "
+                          "CLProgram.build_kernel), compiled by gcc with an OpenMP loop over the work-items (oracle/fake_pyopencl: "
+                          "pyopencl / pocl are not installable), %d pre-marshalled float64 particles x %d launches, + newton.py:14-16 "
+                          "as NumPy array arithmetic; no per-particle Python" % (d["n"], d["reps"])}
+    except Exception as e:  # report, never hide
+        return {"unavailable": repr(e)}
+
+
 def cpu_baseline_block(steps, warmup, budget_s=12.0, with_reference=True):
     """Bounded sample of the default workload: both legs over CPU_SAMPLE particles and the same step window,
     repeated until about budget_s seconds of CPU work have been timed."""
@@ -344,6 +370,7 @@ def cpu_baseline_block(steps, warmup, budget_s=12.0, with_reference=True):
            "kinematics_particle_steps_per_s": last["kinematics_rate"], "photon_particle_steps_per_s": last["photon_rate"]}
     if with_reference:
         out["reference_e2e"] = reference_python()
+        out["reference_kernels"] = reference_kernels()
     return out
 
 
@@ -363,7 +390,7 @@ def run_reference(args):
                                    "float64 C + OpenMP port of the reference's kernels and kinematics (oracle/c/oracle.c); pyopencl / pocl "
                                    "are not installed and not installable here" % (CPU_SAMPLE, args.warmup, args.warmup + args.steps),
                          "kinematics_particle_steps_per_s": r["kinematics_rate"], "photon_particle_steps_per_s": r["photon_rate"],
-                         "reference_e2e": reference_python()},
+                         "reference_e2e": reference_python(), "reference_kernels": reference_kernels()},
         "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

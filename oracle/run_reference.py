@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--n", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--cl-off", action="store_true", help="the reference's pure-Python path (cl_on=False)")
+    ap.add_argument("--kernels", type=int, default=0, metavar="N",
+                    help="kernel-level baseline instead: the reference's own generated scatter kernel on N pre-marshalled particles")
     args = ap.parse_args()
     import numpy as np
 
@@ -40,6 +42,9 @@ def main():
     import physicl.light
     import physicl.newton
 
+    if args.kernels:
+        kernel_level(physicl, np, args.kernels, args.steps)
+        return
     steps = args.steps
     sim = physicl.Simulation(bounds=np.array([1000, 1000, 1000]), cl_on=not args.cl_off, exit=lambda c: len(c.ts) >= steps)
     for _ in range(args.n):
@@ -59,6 +64,61 @@ def main():
     print(json.dumps({"particle_steps_per_s": args.n * rows / wall, "wall_s": wall, "n": args.n, "steps": rows,
                       "cl_on": not args.cl_off, "package": os.path.dirname(physicl.__file__),
                       "last_row": [float(v) for v in sign.data[-1]]}))
+
+
+def kernel_level(physicl, np, n, reps):
+    """the kernel text the reference GENERATES for ScatterIsotropicStep
+    (physicl/light.py:303-315 wrapped by CLProgram.build_kernel, physicl/__init__.py:583-597), compiled by gcc with an
+    OpenMP loop over the work-items (oracle/fake_pyopencl), launched on n pre-marshalled float64 particles, plus the
+    kinematics law of newton.py:14-16 as NumPy array arithmetic over the same n particles (the reference has no kernel
+    for it).  No Python per-particle loops: this is the stand-in for "the reference's OpenCL kernels on the host cores"."""
+    import pyopencl  # the shim
+
+    sim = physicl.Simulation(cl_on=True, exit=lambda c: len(c.ts) >= 1)
+    for _ in range(4):
+        sim.add_obj(physicl.light.PhotonObject(v=np.array([physicl.light.c, 0, 0], dtype=np.double), E=np.double(1)))
+    sim.add_step(0, physicl.UpdateTimeStep(lambda s: np.double(0.001)))
+    sim.add_step(1, physicl.newton.NewtonianKinematicsStep())
+    step = physicl.light.ScatterIsotropicStep(A=np.double(0.001), n=np.double(0.001))
+    sim.add_step(2, step)
+    sim.start()
+    sim.join()  # one timestep: the step has generated and built its kernel
+    prog = step.prog
+    kern = getattr(prog.prog, prog.prog_name)
+    rng = np.random.default_rng(1)
+    c, dt = float(physicl.light.c), 1e-3
+    d = rng.normal(size=(3, n))
+    v = c * d / np.linalg.norm(d, axis=0)
+    r = np.zeros((3, n))
+    args = []
+    for ctype, is_ptr, name in kern.argspec:
+        if is_ptr:
+            if name in ("d0", "d1", "d2"):
+                args.append(np.ascontiguousarray(v[int(name[1])] * dt))
+            elif name == "rtheta":
+                args.append(rng.random(n) * 2 * np.pi)
+            elif name == "rphi":
+                args.append(rng.random(n) * np.pi)
+            elif name == "rand":
+                args.append(rng.random(n))
+            else:
+                args.append(np.empty(n, np.double))  # res0..res2
+        else:
+            args.append(np.double(0.001))  # A, n
+    kern(None, (n,), None, *args)  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        kern(None, (n,), None, *args)
+    t_scatter = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dr = v * dt
+        r += dr
+    t_kin = (time.perf_counter() - t0) / reps
+    hit = int(np.sum(~np.isnan(args[-3])))
+    print(json.dumps({"particle_steps_per_s": n / (t_scatter + t_kin), "scatter_kernel_particles_per_s": n / t_scatter,
+                      "kinematics_numpy_particles_per_s": n / t_kin, "n": n, "reps": reps, "kernel": prog.prog_name,
+                      "scattered_fraction": hit / n, "threads": os.cpu_count()}))
 
 
 if __name__ == "__main__":

@@ -30,6 +30,8 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] == len(os.sched_getaffinity(0)) and cb["sample"]
     ref = cb["reference_e2e"]  # the unmodified reference, end to end (oracle/_ref is built by __graft_entry__.build())
     assert ref.get("kind") == "reference" and ref["value"] > 0 and ref["cores"] == 1, ref
+    rk = cb["reference_kernels"]  # the reference's own generated kernel text on pre-marshalled arrays, all cores
+    assert rk.get("kind") == "reference" and rk["value"] > ref["value"] and rk["scatter_kernel_particles_per_s"] > 0, rk
 
 
 def test_reference_arm_is_silent_on_other_ranks():
