@@ -199,6 +199,30 @@ def test_scatter_flags_match_twin(ctx):
     assert u.same_bits(g.download("x"), host["x"])
 
 
+@pytest.mark.parametrize("k,dt", [(0.0, 1e-3), (1e30, 1e-3), (1.2e-6, 0.0), (3e-39, 1e-3), (float("inf"), 1e-3)])
+def test_collision_test_at_the_ends_of_the_range(ctx, k, dt):
+    """The squared form of pcoll >= rand (|dr|^2 >= (rand/k)^2 with 1/k from the host) at k = 0, k huge, k denormal, k = inf
+    and dt = 0: same rows and bits as the twin, and the law of the reference (light.py:305-307): k = 0 or dt = 0 scatter only
+    on rand = 0 exactly, k huge always."""
+    u = _u()
+    n = 200_003
+    r, v = u.random_photons(n, seed=3)
+    st, g = u.make_store(ctx, r, v, nscat=True)
+    host = u.host_state(g)
+    for step in range(3):
+        got = u.photon_step(ctx, st, g, dt, k, u.C_LIGHT, 0, seed=8, step=step)
+        want = oracle.photon_step_f32(host, dt, k, u.C_LIGHT, 0, seed=8, step=step)
+        assert np.array_equal(got, want), (step, got, want)
+        scat = int(got[oracle.T_SCATTERED])
+        if k >= 1e30:
+            assert scat == n
+        else:
+            ut, up, ur = oracle.philox_uniforms(n, 0, 8, step)
+            assert scat == int((ur == 0).sum())  # a handful at most
+    for nm in host:
+        assert u.same_bits(g.download(nm), host[nm]), nm
+
+
 # ---------------------------------------------------------------------------------------------
 # against the reference's own outputs (golden vectors, injected uniforms)
 # ---------------------------------------------------------------------------------------------
