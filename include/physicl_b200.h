@@ -91,7 +91,9 @@ typedef struct pcl_scatter_params {
 /* Random numbers.  Injected uniforms reproduce the reference, which draws rtheta, rphi, rand per
  * photon on the host (light.py:285, :235, :181); all three arrays hold U[0,1) float32 values
  * (the 2*pi / pi scaling of :285 is applied on the device).  When u_rand is NULL the kernel draws
- * from Philox4x32-10 with key = seed and counter = (global id, step, stream 0). */
+ * from Philox2x32-10: counter = (low word of the global id, step), key = a 32-bit fold of (seed, high
+ * word of the id base); one 64-bit block per photon and timestep gives rand (24 bits), theta (24 bits)
+ * and phi (16 bits).  The global ids of one view must not cross a multiple of 2^32. */
 typedef struct pcl_rng {
     uint64_t seed;
     uint32_t step;

@@ -16,14 +16,15 @@ Retirement policy.  When the pipeline can retire photons (delete scattering, esc
 step runs on the store's ping-pong plane sets through ``pcl_photon_steps_pp``: a launch covers m
 timesteps and writes the survivors of the last one densely into the partner buffer, ALWAYS (a
 compacting launch moves 56 B per slot against 48 B for an in-place one, and neither is the bound).
-Photons that die inside a launch idle in their lanes until it ends (a fraction ~ d (m-1)/2 of the
-issue slots for a death rate d per step) while the load/compaction phase of a launch costs about a
-third of a timestep's instructions: the cost per live photon-step is ~ 1 + d (m-1)/2 + 0.32/m, which is
-flat between m = 4 and m = 8 for the death rates seen here, so m is 8 while (almost) nothing dies and
-4 otherwise.  d comes from the tally rows with a lag: after every chunk (one C-ABI call, about
-``sim.feedback_every`` timesteps) the last row and the device slot counters are copied to pinned host
-memory asynchronously, and the host reads them one or two chunks later (it only ever waits on work the
-GPU has long finished), so the stepping loop has no blocking host<->device round trip.
+Measured launch time at 16 Mi live photons (scripts/time_multi.py): 96 us + 54 us per timestep, i.e. the
+load + compaction phase of a launch costs F = 1.8 timesteps; photons that die inside a launch idle in their
+lanes until it ends (a fraction ~ d (m-1)/2 of the slots for a death rate d per step).  Cost per live
+photon-step ~ (F + m) / (m (1 - d (m-1)/2)): m = 8 wins below d ~ 5 % per step, above it the curve is flat
+between m = 5 and m = 8, so m is 8 while few photons die and 5 otherwise.  d comes from the tally rows
+with a lag: after every chunk (one C-ABI call, about ``sim.feedback_every`` timesteps) the last row and the
+device slot counters are copied to pinned host memory asynchronously, and the host reads them one or two
+chunks later (it only ever waits on work the GPU has long finished), so the stepping loop has no blocking
+host<->device round trip.
 """
 from __future__ import annotations
 
@@ -54,7 +55,7 @@ class FusedPhotonStep(physicl.Step):
         self.retires = bool(escape or scatter.mode & _capi.SCATTER_DELETE)
         # variable-density steps run a run-time compiled kernel (light.py:295-299), in place only
         self.varn = bool(getattr(scatter, "variable_n", False))
-        self.cadence = 4  # m: timesteps per compacting launch (4 or 8, from lagged tally feedback)
+        self.cadence = 5  # m: timesteps per compacting launch (5 or 8, from lagged tally feedback)
         self._fb = []  # pending feedback: (event, pinned int64[18], buffer index at enqueue time)
         self._fb_pool = []
 
@@ -117,9 +118,9 @@ class FusedPhotonStep(physicl.Step):
             if getattr(sim, "compact_cadence", None):
                 self.cadence = int(sim.compact_cadence)
             elif live_in > 0:
-                # two levels are enough (measured flat between 4 and 8 at d = 6.5 %, section 4 of DESIGN.md), and a
-                # stale estimate then costs a few per cent at worst
-                self.cadence = 8 if died / live_in < 0.02 else 4
+                # two levels are enough (the cost curve is flat between 5 and 8 above d ~ 5 %, see the module docstring),
+                # and a stale estimate then costs a few per cent at worst
+                self.cadence = 8 if died / live_in < 0.05 else 5
             self._fb_pool.append(buf)
 
     # ---- roll-back support for Simulation._run_chunked ------------------------------------------------

@@ -381,10 +381,10 @@ def test_fused_plan_is_cached_and_chunks_end_on_compaction_boundaries():
     p3 = s._plan()
     assert p3 is not p1 and len(p3) == 2 and p3[1].measures
     f = p3[1]
-    assert s.feedback_every == 64 and f.cadence == 4
-    for idx, want in ((0, 64), (5, 63), (7, 61), (8, 64)):  # (4 - idx % 4) + 60
+    assert s.feedback_every == 64 and f.cadence == 5
+    for idx, want in ((0, 65), (5, 65), (7, 63), (8, 62)):  # (5 - idx % 5) + 5 * (round(64 / 5) - 1)
         s.step_index = idx
-        assert f.chunk_steps(s) == want and (idx + want) % 4 == 0
+        assert f.chunk_steps(s) == want and (idx + want) % 5 == 0
     s.compact_cadence = 1
     assert f.chunk_steps(s) == 64
     s.compact_cadence, s.feedback_every = None, 8
