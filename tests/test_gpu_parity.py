@@ -548,6 +548,46 @@ def test_errors_are_reported_not_swallowed(ctx):
         _capi.Context(4096)
 
 
+def test_size_limits_are_checked_before_any_launch(ctx):
+    """A view holds fewer than 2^32 slots and its global ids must not cross a multiple of 2^32 (the Philox counter carries
+    the low id word, the key the high one); ids far above 2^32 are fine.  Violations are errors, not wrong numbers."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    r, v = u.beam_photons(64)
+    st, g = u.make_store(ctx, r, v)
+    sp = _capi.ScatterParams(k=1e-6, c=u.C_LIGHT, mode=0)
+    rg = _capi.Rng(seed=1, step=0)
+    pl = _capi.make_planes([])
+    launches = ctx.launches
+
+    def step(soa):
+        soa.dx = soa.dy = soa.dz = None
+        ctx.call("pcl_photon_step", st.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0), C.byref(pl),
+                 st.row_ptr(st.new_row()))
+
+    soa = g.soa()
+    soa.n = 1 << 32
+    with pytest.raises(_capi.PclError, match=r"2\^32 slots"):
+        step(soa)
+    soa = g.soa()
+    soa.id_base = (1 << 32) - 10  # ids [2^32 - 10, 2^32 + 54): crosses
+    with pytest.raises(_capi.PclError, match=r"multiple of 2\^32"):
+        step(soa)
+    assert ctx.launches == launches
+    soa = g.soa()
+    soa.id_base = (7 << 32) + 5  # high word 7 goes into the key
+    step(soa)
+    st.synchronize()
+    assert ctx.launches == launches + 1
+    host = {nm: np.zeros(64, np.float32) for nm in u.PLANE_NAMES}
+    host["vx"][:] = np.float32(u.C_LIGHT)
+    want = oracle.photon_step_f32(host, 1e-3, 1e-6, u.C_LIGHT, 0, seed=1, step=0, id_base=(7 << 32) + 5)
+    assert np.array_equal(st.read_row(st.current_row), want)
+    for nm in u.PLANE_NAMES:
+        assert u.same_bits(g.download(nm), host[nm]), nm
+
+
 # ---------------------------------------------------------------------------------------------
 # retire-and-compact step and the ping-pong multi-step loop
 # ---------------------------------------------------------------------------------------------
