@@ -14,6 +14,9 @@
 #include "pcl_common.cuh"
 
 #define GRAV_JT 256
+#ifndef PCL_GRAV_TMA_DEFAULT
+#define PCL_GRAV_TMA_DEFAULT 0
+#endif
 
 __device__ __forceinline__ float pcl_rsqrt_approx(float x) {
     float y;
@@ -231,6 +234,139 @@ pcl_k_gravity_x2(const float4 *__restrict__ pi, uint64_t n_local, const float4 *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed form of the same kernel.  The j-bodies are first re-packed (pcl_k_gravity_pack: 32 bytes per PAIR,
+// (x0,x1,y0,y1 | z0,z1,m0,m1), bodies to be left out or past the end replaced by a far / massless one, the array padded
+// to whole tiles), so that a 512-body tile is 8 KB of contiguous global memory in exactly the shared-memory layout the
+// inner loop reads.  One thread per CTA streams the tiles with cp.async.bulk into a 3-stage ring; every stage has a
+// "full" mbarrier (completed by the copy engine's byte count) and an "empty" mbarrier (one arrival per warp), so no
+// thread touches a j-body on its way in and the tile loop has no CTA-wide barrier.
+// Measured at 256 Ki bodies: 25.68-25.88 ms against 25.30-25.66 ms for the register-staged kernel above (whose one
+// barrier per tile is 1 % of its stall samples): the kernel is bound by the FP32 pipe, not by how the tiles arrive, and
+// the re-pack pass is extra.  Kept selectable (PCL_GRAV_TMA=1), not the default.
+// ---------------------------------------------------------------------------------------------
+#define GRAV_TJT 512                       /* bodies per tile */
+#define GRAV_TNP (GRAV_TJT / 2)            /* pairs per tile */
+#define GRAV_TSTAGES 3
+#define GRAV_TILE_BYTES (GRAV_TNP * 32)
+
+template <bool UM>
+__global__ void __launch_bounds__(PCL_BLOCK)
+pcl_k_gravity_pack(const float4 *__restrict__ pj, uint64_t n_total, uint64_t skip_lo, uint64_t skip_hi, float4 *pairs,
+                   uint64_t npairs_pad) {
+    const uint64_t stride = (uint64_t)gridDim.x * PCL_BLOCK;
+    const float far = UM ? 1e15f : 0.f;
+    for (uint64_t q = (uint64_t)blockIdx.x * PCL_BLOCK + threadIdx.x; q < npairs_pad; q += stride) {
+        const uint64_t j = 2 * q;
+        const bool l0 = j < n_total && !(j >= skip_lo && j < skip_hi), l1 = j + 1 < n_total && !(j + 1 >= skip_lo && j + 1 < skip_hi);
+        const float4 b0 = l0 ? pj[j] : make_float4(far, far, far, 0.f);
+        const float4 b1 = l1 ? pj[j + 1] : make_float4(far, far, far, 0.f);
+        pairs[2 * q] = make_float4(b0.x, b1.x, b0.y, b1.y);
+        pairs[2 * q + 1] = make_float4(b0.z, b1.z, b0.w, b1.w);
+    }
+}
+
+template <int IB, int T, bool UM, int UNR>
+__global__ void __launch_bounds__(T)
+pcl_k_gravity_tma(const float4 *__restrict__ pi, uint64_t n_local, const ulonglong2 *__restrict__ pairs, uint64_t ntiles,
+                  float G, float eps2, float *ax, float *ay, float *az, int accumulate, float *part) {
+    constexpr int NW = T / 32;
+    __shared__ __align__(128) ulonglong2 s_t[GRAV_TSTAGES][GRAV_TNP * 2];  // pair q: [2q] = (x0,x1),(y0,y1); [2q+1] = (z0,z1),(m0,m1)
+    __shared__ __align__(8) uint64_t s_full[GRAV_TSTAGES], s_empty[GRAV_TSTAGES];
+    const uint64_t i0 = (uint64_t)blockIdx.x * (T * IB) + threadIdx.x;
+    f32x2 xi[IB], yi[IB], zi[IB], axi[IB], ayi[IB], azi[IB];
+#pragma unroll
+    for (int m = 0; m < IB; ++m) {
+        uint64_t i = i0 + (uint64_t)m * T;
+        float4 b = (i < n_local) ? pi[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xi[m] = pk(b.x, b.x);
+        yi[m] = pk(b.y, b.y);
+        zi[m] = pk(b.z, b.z);
+        axi[m] = ayi[m] = azi[m] = pk(0.f, 0.f);
+    }
+    const f32x2 eps = pk(eps2, eps2);
+    const uint64_t k_begin = ntiles * blockIdx.y / gridDim.y, k_end = ntiles * (blockIdx.y + 1) / gridDim.y;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < GRAV_TSTAGES; ++st) {
+            pcl_mbar_init(&s_full[st], 1);
+            pcl_mbar_init(&s_empty[st], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t k) {  // thread 0 only: tile k into stage (k - k_begin) % STAGES
+        const int st = (int)((k - k_begin) % GRAV_TSTAGES);
+        pcl_mbar_expect_tx(&s_full[st], GRAV_TILE_BYTES);
+        pcl_bulk_g2s(&s_t[st][0], pairs + k * (GRAV_TNP * 2), GRAV_TILE_BYTES, &s_full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (uint64_t k = k_begin; k < k_end && k < k_begin + GRAV_TSTAGES - 1; ++k) issue(k);
+    for (uint64_t k = k_begin; k < k_end; ++k) {
+        const uint64_t it = k - k_begin;
+        const int st = (int)(it % GRAV_TSTAGES);
+        if (threadIdx.x == 0) {
+            const uint64_t kn = k + GRAV_TSTAGES - 1;  // goes into the stage that held tile k - 1
+            if (kn < k_end) {
+                if (it >= 1) {
+                    pcl_mbar_wait(&s_empty[(int)((it - 1) % GRAV_TSTAGES)], (uint32_t)(((it - 1) / GRAV_TSTAGES) & 1));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                issue(kn);
+            }
+        }
+        pcl_mbar_wait(&s_full[st], (uint32_t)((it / GRAV_TSTAGES) & 1));
+        const ulonglong2 *tile = s_t[st];
+#pragma unroll UNR
+        for (int q = 0; q < GRAV_TNP; ++q) {
+            const ulonglong2 A = tile[2 * q], B = tile[2 * q + 1];
+#pragma unroll
+            for (int m = 0; m < IB; ++m) {
+                f32x2 dx = sub2(A.x, xi[m]), dy = sub2(A.y, yi[m]), dz = sub2(B.x, zi[m]);
+                f32x2 r2 = fma2(dx, dx, eps);
+                r2 = fma2(dy, dy, r2);
+                r2 = fma2(dz, dz, r2);
+                float lo, hi;
+                upk(r2, lo, hi);
+                f32x2 rinv = pk(pcl_rsqrt_approx(lo), pcl_rsqrt_approx(hi));
+                f32x2 rinv2 = mul2(rinv, rinv);
+                f32x2 sc = UM ? rinv : mul2(B.y, rinv);
+                sc = mul2(sc, rinv2);
+                axi[m] = fma2(sc, dx, axi[m]);
+                ayi[m] = fma2(sc, dy, ayi[m]);
+                azi[m] = fma2(sc, dz, azi[m]);
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) pcl_mbar_arrive(&s_empty[st]);  // this warp is done with the stage
+    }
+#pragma unroll
+    for (int m = 0; m < IB; ++m) {
+        uint64_t i = i0 + (uint64_t)m * T;
+        if (i < n_local) {
+            float a0, a1, b0, b1, c0, c1;
+            upk(axi[m], a0, a1);
+            upk(ayi[m], b0, b1);
+            upk(azi[m], c0, c1);
+            if (part) {  // un-scaled partial sums of this j split; reduced in a fixed order afterwards
+                part[((uint64_t)blockIdx.y * 3 + 0) * n_local + i] = a0 + a1;
+                part[((uint64_t)blockIdx.y * 3 + 1) * n_local + i] = b0 + b1;
+                part[((uint64_t)blockIdx.y * 3 + 2) * n_local + i] = c0 + c1;
+                continue;
+            }
+            float gx = G * (a0 + a1), gy = G * (b0 + b1), gz = G * (c0 + c1);
+            if (accumulate) {
+                gx += ax[i];
+                gy += ay[i];
+                gz += az[i];
+            }
+            ax[i] = gx;
+            ay[i] = gy;
+            az[i] = gz;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PCL_BLOCK)
 pcl_k_gravity_reduce(const float *__restrict__ part, uint32_t nsplit, uint64_t n_local, float G, float *ax, float *ay,
                      float *az, int accumulate) {
@@ -296,6 +432,11 @@ static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local
         (const float4 *)posm_local, n_local, (const float4 *)posm_all, n_total, G, eps2, ax, ay, az, accumulate)
     if (variant >= 1 && variant <= 7)
         PCL_REQUIRE(ctx, j_skip_begin == j_skip_end, "the scalar tuning variants do not implement the skip range");
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char *e = getenv("PCL_GRAV_TMA");  // 1: TMA-fed tiles (re-packed j array), 0: register-staged tiles
+        use_tma = e ? atoi(e) : PCL_GRAV_TMA_DEFAULT;
+    }
     // j splits: enough CTAs for ~4 per SM, at least 2 tiles of 512 bodies per split
     float *part = nullptr;
     unsigned nsplit = 1;
@@ -308,7 +449,9 @@ static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local
         static int per_sm = 0;  // resident CTAs per SM of the default kernel (register-limited), asked once
         if (per_sm == 0) {
             int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcl_k_gravity_x2<2, 128, 512, true, 8>, 128, 0) != cudaSuccess || nb < 1) nb = 7;
+            cudaError_t oe = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcl_k_gravity_tma<2, 128, true, 8>, 128, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pcl_k_gravity_x2<2, 128, 512, true, 8>, 128, 0);
+            if (oe != cudaSuccess || nb < 1) nb = 7;
             per_sm = nb;
         }
         const uint64_t slots = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
@@ -319,8 +462,9 @@ static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local
         for (uint64_t sp = 1; sp <= hi; ++sp) {
             const double waves = (double)(itiles * sp) / (double)slots;
             const double full = (double)(uint64_t)(waves + 0.999999);
-            // fill of the last wave, with a mild preference for about 6 waves (splits cost a partial-sum pass)
-            const double score = waves / full - 0.004 * (waves > 6.0 ? waves - 6.0 : 6.0 - waves);
+            // fill of the last wave, with a mild preference for about 16 waves (measured at 256 Ki bodies: 16 splits 25.30 ms,
+            // 8 splits 25.66 ms; more splits only add to the partial-sum pass)
+            const double score = waves / full - 0.001 * (waves > 16.0 ? waves - 16.0 : 16.0 - waves);
             if (score > best) {
                 best = score;
                 want = sp;
@@ -357,6 +501,39 @@ static int gravity_accel(pcl_ctx *ctx, uintptr_t stream, const float *posm_local
         if (uniform_mass) PCL_GRAV2U(IB, T, JT, true, 4);        \
         else PCL_GRAV2U(IB, T, JT, false, 4);                    \
     } while (0)
+    if (use_tma && variant == 0) {
+        const uint64_t ntiles = (n_total + GRAV_TJT - 1) / GRAV_TJT;
+        const uint64_t npairs_pad = ntiles * GRAV_TNP;
+        if (ctx->grav_pairs_cap < npairs_pad) {
+            if (ctx->grav_pairs) PCL_CUDA(ctx, cudaFree(ctx->grav_pairs));
+            ctx->grav_pairs = nullptr;
+            ctx->grav_pairs_cap = 0;
+            PCL_CUDA(ctx, cudaMalloc(&ctx->grav_pairs, npairs_pad * 32));
+            ctx->grav_pairs_cap = npairs_pad;
+        }
+        const unsigned pgrid = pcl_stream_grid(ctx, npairs_pad, PCL_BLOCK, 8);
+        const dim3 grid((unsigned)((n_local + 255) / 256), nsplit);
+        if (uniform_mass) {
+            pcl_k_gravity_pack<true><<<pgrid, PCL_BLOCK, 0, st>>>((const float4 *)posm_all, n_total, j_skip_begin, j_skip_end,
+                                                                  (float4 *)ctx->grav_pairs, npairs_pad);
+            PCL_LAUNCHED(ctx);
+            pcl_k_gravity_tma<2, 128, true, 8><<<grid, 128, 0, st>>>((const float4 *)posm_local, n_local, (const ulonglong2 *)ctx->grav_pairs,
+                                                                     ntiles, G, eps2, ax, ay, az, accumulate, part);
+        } else {
+            pcl_k_gravity_pack<false><<<pgrid, PCL_BLOCK, 0, st>>>((const float4 *)posm_all, n_total, j_skip_begin, j_skip_end,
+                                                                   (float4 *)ctx->grav_pairs, npairs_pad);
+            PCL_LAUNCHED(ctx);
+            pcl_k_gravity_tma<2, 128, false, 8><<<grid, 128, 0, st>>>((const float4 *)posm_local, n_local, (const ulonglong2 *)ctx->grav_pairs,
+                                                                      ntiles, G, eps2, ax, ay, az, accumulate, part);
+        }
+        PCL_LAUNCHED(ctx);
+        if (part) {
+            unsigned rgrid = pcl_stream_grid(ctx, n_local, PCL_BLOCK, 8);
+            pcl_k_gravity_reduce<<<rgrid, PCL_BLOCK, 0, st>>>(part, nsplit, n_local, G, ax, ay, az, accumulate);
+            PCL_LAUNCHED(ctx);
+        }
+        return 0;
+    }
     switch (variant) {
         case 1: PCL_GRAV(4, 128); break;
         case 2: PCL_GRAV(2, 128); break;

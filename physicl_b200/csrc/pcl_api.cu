@@ -85,6 +85,7 @@ extern "C" int pcl_destroy(pcl_ctx *ctx) {
     pcl_hostpipe_destroy(ctx);
     if (ctx->scan_buf) cudaFree(ctx->scan_buf);
     if (ctx->grav_part) cudaFree(ctx->grav_part);
+    if (ctx->grav_pairs) cudaFree(ctx->grav_pairs);
     if (ctx->trig) cudaFree(ctx->trig);
     free(ctx);
     return 0;

@@ -38,6 +38,9 @@ struct pcl_ctx {
     // gravity: partial accelerations of the j splits
     float *grav_part;
     size_t grav_cap;
+    // gravity, TMA-fed form: the j-bodies re-packed pair by pair, padded to whole tiles
+    void *grav_pairs;
+    size_t grav_pairs_cap;
     pcl_hostpipe *pipe;
     // (sin, cos)(2 pi k / 512): the direction table of the photon kernels (pcl_device.cuh), built at pcl_init
     float *trig;

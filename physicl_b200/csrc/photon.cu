@@ -72,33 +72,6 @@ pcl_k_photon_step(pcl_soa p, StepK K, int64_t *row) {
 // memory system is kept busy by the copy engine and not by however many warps happen to be waiting.
 // Two stages per CTA (2 x planes x 4 KB).  Stores go straight from registers (STG.128).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pcl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pcl_mbar_init(uint64_t *b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pcl_smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void pcl_mbar_expect_tx(uint64_t *b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pcl_smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void pcl_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     pcl_smem_u32(dst)),
-                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(pcl_smem_u32(b))
-                 : "memory");
-}
-__device__ __forceinline__ void pcl_mbar_wait(uint64_t *b, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "PCL_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra PCL_DONE_%=;\n"
-        "bra PCL_WAIT_%=;\n"
-        "PCL_DONE_%=:\n"
-        "}\n" ::"r"(pcl_smem_u32(b)),
-        "r"(parity)
-        : "memory");
-}
-
 #define PCL_WTILE_SLOTS 128                      /* one warp-tile: 4 photons per lane */
 #define PCL_WPLANE_BYTES (PCL_WTILE_SLOTS * 4)   /* 512 B of one plane */
 
