@@ -646,12 +646,15 @@ def leg_e2e(args, rank, world, local, n, id_base):
         wall = time.perf_counter() - t0
         barrier_sync(world)
         wall = max_over_ranks(wall, world)
-        return sum_over_ranks(float(state["live"]), world) / wall, state["up"] // k, state["down"] // k
+        # PCIe rate of this rank's link, both directions at once (the measured bidirectional ceiling is in profiles/bench_r1/pcie_peak.txt)
+        link = {"h2d_GBps": state["up"] / wall / 1e9, "d2h_GBps": state["down"] / wall / 1e9}
+        return sum_over_ranks(float(state["live"]), world) / wall, state["up"] // k, state["down"] // k, link
 
-    v8, up8, down8 = measure(8, args.steps)
+    v8, up8, down8, link8 = measure(8, args.steps)
     k1 = max(3, min(args.steps, 6))
-    v1, up1, down1 = measure(1, k1)
+    v1, up1, down1, link1 = measure(1, k1)
     return {"value": v8, "unit": "particle-steps/s", "h2d_bytes_per_step": up8, "d2h_bytes_per_step": down8, "steps": args.steps,
+            "pcie_per_gpu": link8,
             "timesteps_per_round_trip": 8, "photons_per_gpu": n,
             "timer": "host wall clock around the synchronous C-ABI calls, max over ranks",
             "path": "pcl_photon_steps_host_compact: pinned host SoA planes (r, v, id) -> 1 Mi-photon chunks H2D -> ONE fused launch "
@@ -661,6 +664,7 @@ def leg_e2e(args, rank, world, local, n, id_base):
             "sample": "the first %d photons of each rank's block (the path streams 1 Mi-photon chunks: its throughput does not depend "
                       "on the block size)" % n,
             "one_timestep_per_round_trip": {"value": v1, "h2d_bytes_per_step": up1, "d2h_bytes_per_step": down1, "steps": k1,
+                                            "pcie_per_gpu": link1,
                                             "path": "pcl_photon_step_host_compact: the same, planes back in host memory after EVERY timestep "
                                                     "(28 B up + 28 B down per photon-step over PCIe)"}}
 

@@ -24,16 +24,6 @@ __device__ __forceinline__ float pcl_rsqrt_approx(float x) {
     return y;
 }
 
-__device__ __forceinline__ void pcl_cp_async16(void *smem, const void *gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void pcl_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void pcl_cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N));
-}
-
 template <int IB, int GRAV_THREADS>
 __global__ void __launch_bounds__(GRAV_THREADS)
 pcl_k_gravity(const float4 *__restrict__ pi, uint64_t n_local, const float4 *__restrict__ pj, uint64_t n_total,

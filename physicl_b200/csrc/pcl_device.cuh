@@ -240,5 +240,16 @@ __device__ __forceinline__ void pcl_mbar_arrive(uint64_t *b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pcl_smem_u32(b)) : "memory");
 }
 
+// per-thread asynchronous 16-byte copies global -> shared (LDGSTS), grouped and awaited by the issuing thread
+__device__ __forceinline__ void pcl_cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void pcl_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void pcl_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float &pcl_f4(float4 &v, int i) { return (&v.x)[i]; }
 __device__ __forceinline__ uint32_t &pcl_u4(uint4 &v, int i) { return (&v.x)[i]; }

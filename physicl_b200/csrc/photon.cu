@@ -203,6 +203,9 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 // Traffic per live photon and launch: read r,v,id 28 B + write r,v,id 28 B (+ e, nscat when present).
 // !COMPACT: in place; r is always written, v and nscat only by groups in which a photon scattered.
 // ---------------------------------------------------------------------------------------------
+#ifndef PCL_MULTI_PREFETCH_DEFAULT
+#define PCL_MULTI_PREFETCH_DEFAULT 0
+#endif
 #ifndef PCL_MULTI_MINB_COMPACT
 #define PCL_MULTI_MINB_COMPACT 4
 #endif
@@ -211,8 +214,11 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 #endif
 template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
 __global__ void __launch_bounds__(PCL_BLOCK, COMPACT ? PCL_MULTI_MINB_COMPACT : PCL_MULTI_MINB_INPLACE)
-pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps) {
+pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps, int prefetch) {
     constexpr int NST = COMPACT ? 9 : 1;  // staged planes: x y z vx vy vz id nscat e
+    // prefetch: every thread copies ITS 16-byte pieces of the CTA's next tile into shared memory with cp.async while the
+    // current tile is being stepped, and picks them up (its own slots: no barrier) at the top of the next iteration
+    extern __shared__ __align__(16) float4 s_pf[];  // [plane][PCL_BLOCK], planes x y z vx vy vz [id] [e] [nscat]
     __shared__ __align__(16) float s_stage[NST][COMPACT ? PCL_BLOCK * 4 + 32 : 4];
     __shared__ uint32_t s_warp[PCL_WARPS];
     __shared__ unsigned long long s_base;
@@ -229,6 +235,28 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
     const bool carry_e = COMPACT && !WAVE && s.e != nullptr && d.e != nullptr;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t base_lo = (uint32_t)s.id_base;
+    const bool use_pf = prefetch != 0 && !INJ;
+    const int pq_id = 6, pq_e = 6 + (has_id ? 1 : 0), pq_ns = pq_e + (WAVE ? 1 : 0);
+    auto pf_issue = [&](uint64_t t) {
+        const uint64_t ii = (t * PCL_BLOCK + threadIdx.x) * 4;
+        float4 *slot = s_pf + threadIdx.x;
+        pcl_cp_async16(slot + 0 * PCL_BLOCK, s.x + ii);
+        pcl_cp_async16(slot + 1 * PCL_BLOCK, s.y + ii);
+        pcl_cp_async16(slot + 2 * PCL_BLOCK, s.z + ii);
+        pcl_cp_async16(slot + 3 * PCL_BLOCK, s.vx + ii);
+        pcl_cp_async16(slot + 4 * PCL_BLOCK, s.vy + ii);
+        pcl_cp_async16(slot + 5 * PCL_BLOCK, s.vz + ii);
+        if (has_id) pcl_cp_async16(slot + pq_id * PCL_BLOCK, s.id + ii);
+        if (WAVE) pcl_cp_async16(slot + pq_e * PCL_BLOCK, s.e + ii);
+        if (has_ns) pcl_cp_async16(slot + pq_ns * PCL_BLOCK, s.nscat + ii);
+        pcl_cp_async_commit();
+    };
+    auto whole = [&](uint64_t t) { return (t + 1) * (uint64_t)(PCL_BLOCK * 4) <= n; };  // every slot of tile t is valid
+    bool pre = false;  // the current tile sits in s_pf
+    if (use_pf && blockIdx.x < ntiles && whole(blockIdx.x)) {
+        pf_issue(blockIdx.x);
+        pre = true;
+    }
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t i = (tile * PCL_BLOCK + threadIdx.x) * 4;
         float4 x, y, z, vx, vy, vz, e = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -237,7 +265,17 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
         float4 ut4, up4, ur4;
         const float qnan = __int_as_float(0x7fc00000);
         const bool full = i + 3 < n;
-        if (full) {
+        const uint64_t next_tile = tile + gridDim.x;
+        const bool pre_next = use_pf && next_tile < ntiles && whole(next_tile);
+        if (pre) {
+            pcl_cp_async_wait<0>();
+            const float4 *slot = s_pf + threadIdx.x;
+            x = slot[0 * PCL_BLOCK], y = slot[1 * PCL_BLOCK], z = slot[2 * PCL_BLOCK];
+            vx = slot[3 * PCL_BLOCK], vy = slot[4 * PCL_BLOCK], vz = slot[5 * PCL_BLOCK];
+            if (has_id) id = *reinterpret_cast<const uint4 *>(slot + pq_id * PCL_BLOCK);
+            if (WAVE) e = slot[pq_e * PCL_BLOCK];
+            if (has_ns) nsc = *reinterpret_cast<const uint4 *>(slot + pq_ns * PCL_BLOCK);
+        } else if (full) {
             x = pcl_ld4(s.x + i), y = pcl_ld4(s.y + i), z = pcl_ld4(s.z + i);
             vx = pcl_ld4(s.vx + i), vy = pcl_ld4(s.vy + i), vz = pcl_ld4(s.vz + i);
             if (WAVE) e = pcl_ld4(s.e + i);
@@ -272,7 +310,7 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
                 }
             }
         }
-        bool any_scat = false;
+        bool any_scat = false, issued = false;
         for (uint32_t st = 0; st < nsteps; ++st) {
             // all four photons of every lane of this warp retired: nothing left to do for the warp
             const bool alive = (x.x == x.x) || (x.y == x.y) || (x.z == x.z) || (x.w == x.w);
@@ -297,7 +335,13 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
                 pcl_u4(nsc, l) += sc ? 1u : 0u;
             }
             pcl_tally_to_shared<PL>(t, s_acc[st]);
+            if (st == 0 && pre_next) {  // the slots' old contents are in registers and have been used
+                pf_issue(next_tile);
+                issued = true;
+            }
         }
+        if (pre_next && !issued) pf_issue(next_tile);  // a warp whose photons were all retired left the loop at once
+        pre = pre_next;
         if (!COMPACT) {
             if (full) {
                 pcl_st4(s.x + i, x);
@@ -587,6 +631,16 @@ static uint32_t photon_fuse_max() {
     return (uint32_t)fuse;
 }
 
+// PCL_MULTI_PREFETCH=1: the fused kernel prefetches its next tile with cp.async (tuning aid; see the kernel)
+static int multi_prefetch() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PCL_MULTI_PREFETCH");
+        v = e ? atoi(e) : PCL_MULTI_PREFETCH_DEFAULT;
+    }
+    return v;
+}
+
 template <bool WAVE, bool DEL, bool INJ, bool PL>
 static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, const pcl_soa *dst, const StepK &K,
                             int64_t *row, uint64_t *n_out, uint32_t nsteps, bool keep_count) {
@@ -598,8 +652,11 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         PCL_REQUIRE(ctx, aligned, "the compacting step needs 16-byte aligned planes");
         if (!keep_count) PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
-        pcl_k_photon_multi<WAVE, DEL, INJ, PL, true><<<grid, PCL_BLOCK, 0, st>>>(p, *dst, K, row, (unsigned long long *)n_out,
-                                                                                  nsteps);
+        const int pf = multi_prefetch() && !INJ;
+        const size_t smem = pf ? (size_t)(6 + (p.id ? 1 : 0) + (WAVE ? 1 : 0) + (p.nscat ? 1 : 0)) * PCL_BLOCK * sizeof(float4) : 0;
+        auto kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, true>;
+        if (pf) PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PCL_BLOCK, smem, st>>>(p, *dst, K, row, (unsigned long long *)n_out, nsteps, pf);
         PCL_LAUNCHED(ctx);
         return 0;
     }
@@ -614,7 +671,11 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
     if (nsteps > 1 || (single_multi && aligned && !INJ)) {  // several timesteps per HBM round trip, in place
         PCL_REQUIRE(ctx, aligned, "multi-step launches need 16-byte aligned planes");
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
-        pcl_k_photon_multi<WAVE, DEL, INJ, PL, false><<<grid, PCL_BLOCK, 0, st>>>(p, p, K, row, nullptr, nsteps);
+        const int pf = multi_prefetch() && !INJ;
+        const size_t smem = pf ? (size_t)(6 + (p.id ? 1 : 0) + (WAVE ? 1 : 0) + (p.nscat ? 1 : 0)) * PCL_BLOCK * sizeof(float4) : 0;
+        auto kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, false>;
+        if (pf) PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PCL_BLOCK, smem, st>>>(p, p, K, row, nullptr, nsteps, pf);
         PCL_LAUNCHED(ctx);
         return 0;
     }
