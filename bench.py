@@ -647,7 +647,10 @@ def leg_e2e(args, rank, world, local, n, id_base):
         barrier_sync(world)
         wall = max_over_ranks(wall, world)
         # PCIe rate of this rank's link, both directions at once (the measured bidirectional ceiling is in profiles/bench_r1/pcie_peak.txt)
-        link = {"h2d_GBps": state["up"] / wall / 1e9, "d2h_GBps": state["down"] / wall / 1e9}
+        link = {"h2d_GBps": state["up"] / wall / 1e9, "d2h_GBps": state["down"] / wall / 1e9,
+                # what the host's memory system sustains for all ranks' DMA together (reads + writes of pinned memory): this, not
+                # the link, bounds the N-GPU figure on a box whose GPUs hang off one NUMA node
+                "host_dram_GBps_all_gpus": sum_over_ranks(float(state["up"] + state["down"]), world) / wall / 1e9}
         return sum_over_ranks(float(state["live"]), world) / wall, state["up"] // k, state["down"] // k, link
 
     v8, up8, down8, link8 = measure(8, args.steps)

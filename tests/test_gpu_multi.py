@@ -18,4 +18,6 @@ def test_two_rank_sharded_runs_match_single_gpu():
            "--master-port", "29611", os.path.join(here, "mp_sharded_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "photon shard check: ok" in r.stdout and "gravity shard check: ok" in r.stdout
+    assert "photon shard check: ok" in r.stdout, r.stdout[-3000:]
+    for mode, used in (("p2p", "GravityExchangeP2P"), ("nccl", "GravityExchange")):  # both exchanges, and the one asked for ran
+        assert "gravity shard check (%s -> %s): ok" % (mode, used) in r.stdout, r.stdout[-3000:]
