@@ -206,7 +206,8 @@ int pcl_compact(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *src, const pcl_so
 /* planck_phot_distribution (light.py:73-104): inverse-CDF draw on the reference's binned law.
  * cdf: device float64[ncdf] (= bins-1 cumulative masses, light.py:88-93); grid energy of bin x
  * is e_min + x*(e_max-e_min)/(bins-1) scaled by 1/E0 by the caller (e_lo, e_step are in E0 units).
- * bin_out (nullable) gets x, or -1 where the reference falls off its loop and returns None. */
+ * bin_out (nullable) gets x, or -1 where the reference falls off its loop and returns None.
+ * Uniform of photon gid = id_base + i: word gid & 3 of Philox4x32-10(counter (gid >> 2, 0, 1), key seed), top 24 bits. */
 int pcl_planck_sample(pcl_ctx *ctx, uintptr_t stream, uint64_t n, uint64_t id_base, uint64_t seed,
                       const double *cdf, uint32_t ncdf, float e_lo, float e_step, float *e_out,
                       int32_t *bin_out);

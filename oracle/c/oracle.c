@@ -396,14 +396,18 @@ void orc_tally_f32(uint64_t n, const float *x, const float *y, const float *z, c
     }
 }
 
-/* light.py:101-104 on a prebuilt CDF; uniform from Philox stream 1 */
+/* light.py:101-104 on a prebuilt CDF; uniform from Philox4x32 stream 1, one block per four photons */
 void orc_planck_sample(uint64_t n, uint64_t id_base, uint64_t seed, const double *cdf, uint32_t ncdf, float e_lo,
                        float e_step, float *e_out, int32_t *bin_out) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
-        float a, b, c;
-        draw3(id_base + (uint64_t)i, seed, 0u, 1u, &a, &b, &c);
-        double u = (double)a;
+        /* photon gid takes word gid & 3 of the Philox4x32-10 block with counter (gid >> 2, step 0, stream 1) */
+        const uint64_t gid = id_base + (uint64_t)i, q = gid >> 2;
+        uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), 0u, 1u};
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t o[4];
+        orc_philox4x32_10(ctr, key, o);
+        double u = (double)u01(o[gid & 3u]);
         int32_t bin = -1;
         /* the reference's own linear scan, verbatim in meaning: first x>=1 with cdf[x]>=u>=cdf[x-1] */
         for (uint32_t xq = 1; xq < ncdf; ++xq) {

@@ -117,8 +117,8 @@ def planck_phot_distribution(E_min, E_max, T, bins=1000):
 
 
 def planck_sample_device(ctx, n, E_min, E_max, T, bins=1000, seed=0, id_base=0, device=None, want_bins=False, timing=None):
-    """Device form of the same sampler for bulk emission: one Philox uniform per photon (stream 1),
-    binary search of the float64 table.  Returns ``(e, E0[, bin])``: ``e`` is a float32 CUDA tensor of
+    """Device form of the same sampler for bulk emission: one Philox4x32 block per four photons (stream 1),
+    guide-table look-up of the float64 table (held as integers in shared memory when it fits).  Returns ``(e, E0[, bin])``: ``e`` is a float32 CUDA tensor of
     ``E / E0`` with ``E0 = E_max``; ``bin`` (int32) is the grid index, -1 where the reference yields None.
     ``timing``: a dict that receives ``device_ms``, the CUDA-event time of the sampling launches."""
     import torch

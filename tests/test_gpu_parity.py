@@ -371,6 +371,63 @@ def test_planck_bins_bit_exact_and_chi_square(ctx, golden):
     assert abs((b < 0).mean() - norm[0]) < 5 * np.sqrt(norm[0] / n) + 1e-6  # None rate = mass of interval 0
 
 
+def _planck_case_cdf(kind, ncdf):
+    rng = np.random.default_rng(ncdf)
+    if kind == "uniform":  # every bucket of the guide table holds about ncdf / 65536 thresholds
+        w = rng.uniform(0.5, 1.5, ncdf)
+    elif kind == "tails":  # almost all mass in a few entries: thousands of thresholds share one bucket
+        w = np.full(ncdf, 1e-9)
+        w[rng.integers(0, ncdf, 7)] = 1.0
+    elif kind == "over_one":  # cumulative sums that reach and pass 1 before the table ends
+        w = rng.uniform(0.5, 1.5, ncdf)
+        w[-ncdf // 50:] = 0.0
+    else:  # entries that are exact multiples of 2^-24 (u == cdf[x] must be accepted: closed interval)
+        w = rng.integers(1, 64, ncdf).astype(np.float64)
+        return np.cumsum(w / 2.0 ** 24 * np.floor(2.0 ** 24 / w.sum()))
+    cdf = np.cumsum(w / w.sum())
+    if kind == "over_one":
+        cdf = cdf * (1.0 + 3e-16) + 1e-16
+        assert (cdf >= 1.0).sum() > 10
+    return cdf
+
+
+@pytest.mark.parametrize("kind,ncdf,n,id_base", [
+    ("uniform", 49_999, 300_000, 0),        # shared-memory tables, 16-byte stores
+    ("uniform", 49_999, 300_001, 2 ** 33 + 5),  # ... blocks cut by both ends of the shard, scalar stores, high id word
+    ("uniform", 65_535, 270_000, 4),        # largest table that fits the shared-memory form
+    ("uniform", 65_536, 270_000, 4),        # one more: guide in global memory, float64 probes
+    ("uniform", 199, 1_000_003, 0),         # bins=200 of the reference's examples: most buckets empty
+    ("tails", 30_000, 400_000, 8),          # crowded buckets: the byte search
+    ("over_one", 20_000, 400_000, 0),
+    ("grid", 5_000, 2_000_000, 0),          # equality with table entries
+    ("uniform", 1, 300_000, 0),             # a one-entry table never yields a bin (the reference needs x >= 1)
+    ("uniform", 49_999, 1, 3), ("uniform", 49_999, 5, 3), ("uniform", 49_999, 4097, 1),  # small draws
+])
+def test_planck_sampler_forms_bit_exact_vs_linear_scan(ctx, kind, ncdf, n, id_base):
+    """Both kernel forms of pcl_planck_sample (tables in shared memory / guide in global memory) against the oracle's
+    linear scan of the reference's rule (light.py:101-104) on synthetic tables that stress each branch."""
+    cdf = _planck_case_cdf(kind, ncdf)
+    dev = torch.device("cuda", ctx.device)
+    cdf_d = torch.from_numpy(cdf).to(dev)
+    pad = 64
+    e = torch.full((n + 2 * pad,), -7.0, dtype=torch.float32, device=dev)
+    b = torch.full((n + 2 * pad,), -7, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ctx.call("pcl_planck_sample", stream, C.c_uint64(n), C.c_uint64(id_base), C.c_uint64(99), C.c_void_p(cdf_d.data_ptr()),
+             C.c_uint32(ncdf), C.c_float(0.25), C.c_float(1e-5), C.c_void_p(e[pad:].data_ptr()), C.c_void_p(b[pad:].data_ptr()))
+    torch.cuda.synchronize()
+    e, b = e.cpu().numpy(), b.cpu().numpy()
+    assert (b[:pad] == -7).all() and (b[pad + n:] == -7).all() and (e[:pad] == -7).all() and (e[pad + n:] == -7).all()
+    e, b = e[pad:pad + n], b[pad:pad + n]
+    e_or, b_or = oracle.planck_sample(n, id_base, 99, cdf, np.float32(0.25), np.float32(1e-5))
+    assert np.array_equal(b, b_or)
+    assert np.array_equal(np.isnan(e), b < 0) and _u().same_bits(e[b >= 0], e_or[b >= 0])
+    if kind == "grid" :
+        # the closed interval of the reference: some uniforms equal a table entry and must take the LOWER bin
+        m = np.round(cdf * 2.0 ** 24).astype(np.int64)
+        assert np.array_equal(m / 2.0 ** 24, cdf)
+
+
 # ---------------------------------------------------------------------------------------------
 # stochastic parity: the reference's distributions (KS / chi-square at fixed sample size)
 # ---------------------------------------------------------------------------------------------
