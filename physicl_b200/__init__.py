@@ -40,6 +40,16 @@ class Step:
     def __init__(self):
         pass
 
+    def __compile_cl__(self, sim):
+        """physicl/__init__.py:300-304: hook for a step's kernel build; a no-op in the base class, as there."""
+        pass
+
+    def __run_cl(self, sim):
+        pass
+
+    def __run_py(self, sim):
+        pass
+
     def run(self, sim):
         pass
 
