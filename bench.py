@@ -355,6 +355,26 @@ def reference_kernels(n=1_000_000, reps=10, timeout=240):
         return {"unavailable": repr(e)}
 
 
+def dropin_objects(n=10000, steps=10):
+    """The script cpu_baseline.reference_e2e times on the unmodified reference, here with only the import changed
+    (scripts/dropin_objects.py): n PhotonObjects added one by one, sim.start(); sim.join(), every object current on the
+    host again at the end.  Host wall clock; the Python object bridge, not the GPU, is what it measures."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import dropin_objects as script
+
+        script.run(256, 2)  # context, module load
+        best = min((script.run(n, steps) for _ in range(3)), key=lambda d: d["wall_s"])
+        return {"value": best["particle_steps_per_s"], "unit": "particle-steps/s", "n": best["n"], "steps": best["steps"],
+                "wall_s": best["wall_s"], "run_s": best["run_s"], "pull_s": best["pull_s"], "last_row": best["last_row"],
+                "timer": "host wall clock from sim.start() until every PhotonObject is current on the host again (best of 3)",
+                "path": "sim.add_obj x n -> device store built from the objects -> chunked fused launches -> one D2H of the "
+                        "planes -> per-object attribute writes; compare with cpu_baseline.reference_e2e (same script, "
+                        "unmodified reference)"}
+    except Exception as e:  # report, never hide
+        return {"unavailable": repr(e)}
+
+
 def cpu_baseline_block(steps, warmup, budget_s=12.0, with_reference=True):
     """Bounded sample of the default workload: both legs over CPU_SAMPLE particles and the same step window,
     repeated until about budget_s seconds of CPU work have been timed."""
@@ -968,6 +988,7 @@ def main():
     out["clocks"] = clocks.summary() if rank == 0 else None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "sweep_1b":
         out["cpu_baseline"] = cpu_baseline_block(args.steps, args.warmup)
+        out["dropin_objects"] = dropin_objects()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -13,6 +13,7 @@ physicl/__init__.py:413) needs the built library and a B200; device steps raise 
 from __future__ import annotations
 
 import copy
+import gc
 import os
 import threading
 import time
@@ -361,6 +362,17 @@ class Simulation(threading.Thread):
         self._device_dirty = False
         st = self.store
         keep = []
+        gc_was_on = gc.isenabled()
+        gc.disable()  # millions of small allocations and no cycles: the collector's generation scans would double the time
+        try:
+            self._pull_groups(st, keep)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        list.clear(self.objects)
+        list.extend(self.objects, keep)
+
+    def _pull_groups(self, st, keep):
         for kind, g in st.groups.items():
             snap = st.snapshot(kind, live_only=True)
             fresh = g.host_objs is None
@@ -374,29 +386,44 @@ class Simulation(threading.Thread):
                     Object.__init__(o)
                     o._pcl_origin = (id(st), kind, int(i))  # which bulk particle this object stands for
                     g.host_objs[int(i)] = o
-            for j, i in enumerate(snap["id"]):
-                o = g.host_objs[int(i)]
-                v_new = np.array([snap["vx"][j], snap["vy"][j], snap["vz"][j]], np.float64)
-                # Object.dv (physicl/__init__.py:392; written by the scatter step, light.py:325-331: v_new - v_old for a
-                # photon that scattered, zero otherwise): the change of v since the object was last current on the host.
-                # With a host step in the pipeline that is once per timestep, i.e. exactly the reference's value.
-                dv = np.zeros(3) if fresh else v_new - np.asarray(o.v, np.float32).astype(np.float64)  # state is binary32 on the device
-                o.dv = Measurement(dv, "")
-                o.dv.scale, o.dv.units, o.dv.original_units = np.double(1), {"L": 1, "T": -1}, {"m": 1, "s": -1}
-                o.r = Measurement([snap["x"][j], snap["y"][j], snap["z"][j]], "")
-                o.r.scale, o.r.units, o.r.original_units = np.double(1), {"L": 1}, {"m": 1}
-                o.v = Measurement(v_new, "")
-                o.v.scale, o.v.units, o.v.original_units = np.double(1), {"L": 1, "T": -1}, {"m": 1, "s": -1}
-                if "dx" in snap:
-                    o.dr = Measurement([snap["dx"][j], snap["dy"][j], snap["dz"][j]], "")
-                    o.dr.scale, o.dr.units, o.dr.original_units = np.double(1), {"L": 1}, {"m": 1}
-                if "E" in snap and kind == "photon":
-                    o.E = np.double(snap["E"][j])
-                if "nscat" in snap:
-                    o.nscat = int(snap["nscat"][j])
-                keep.append(o)
-        list.clear(self.objects)
-        list.extend(self.objects, keep)
+            # whole-group arrays first, then one row view per attribute and object (a Measurement built from a list
+            # parses units and copies; with 10^4..10^6 objects that was most of the wall time of a pulled run)
+            ids = [int(i) for i in snap["id"]]
+            objs = [g.host_objs[i] for i in ids]
+            n_o = len(objs)
+            one = np.double(1)
+            V = np.stack([snap["vx"], snap["vy"], snap["vz"]], axis=1).astype(np.float64) if n_o else np.zeros((0, 3))
+            R = np.stack([snap["x"], snap["y"], snap["z"]], axis=1).astype(np.float64) if n_o else np.zeros((0, 3))
+            # Object.dv (physicl/__init__.py:392; written by the scatter step, light.py:325-331: v_new - v_old for a
+            # photon that scattered, zero otherwise): the change of v since the object was last current on the host.
+            # With a host step in the pipeline that is once per timestep, i.e. exactly the reference's value.
+            if fresh or not n_o:
+                DV = np.zeros((n_o, 3))
+            else:  # state is binary32 on the device
+                DV = V - np.array([o.v for o in objs], dtype=np.float64).reshape(n_o, 3).astype(np.float32).astype(np.float64)
+            DR = np.stack([snap["dx"], snap["dy"], snap["dz"]], axis=1).astype(np.float64) if "dx" in snap and n_o else None
+            E = snap["E"] if "E" in snap and kind == "photon" else None
+            NS = snap["nscat"] if "nscat" in snap else None
+            M = Measurement
+            for j, o in enumerate(objs):
+                m = DV[j].view(M)
+                m.scale, m.units, m.original_units = one, {"L": 1, "T": -1}, {"m": 1, "s": -1}
+                o.dv = m
+                m = R[j].view(M)
+                m.scale, m.units, m.original_units = one, {"L": 1}, {"m": 1}
+                o.r = m
+                m = V[j].view(M)
+                m.scale, m.units, m.original_units = one, {"L": 1, "T": -1}, {"m": 1, "s": -1}
+                o.v = m
+                if DR is not None:
+                    m = DR[j].view(M)
+                    m.scale, m.units, m.original_units = one, {"L": 1}, {"m": 1}
+                    o.dr = m
+                if E is not None:
+                    o.E = np.double(E[j])
+                if NS is not None:
+                    o.nscat = int(NS[j])
+            keep.extend(objs)
 
     # ---- main loop (physicl/__init__.py:501-524) ----------------------------------------------
     def _plan(self):

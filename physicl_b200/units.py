@@ -14,6 +14,7 @@ Behaviour kept from the reference (its test/test_units.py is the specification):
 from __future__ import annotations
 
 import copy
+import operator
 import re
 
 import numpy as np
@@ -55,6 +56,9 @@ _DERIVED = {
     "eV": (1.602176634e-19, (("J", 1),)),
 }
 
+_PARSED = {}  # Measurement._apply_units: parsed unit strings
+_ONE = np.double(1)
+_FIRST = operator.itemgetter(0)
 _TOKEN = re.compile(r"([a-zA-Z]+)\s*(?:\*\*|\^)\s*(-?\d+(?:\.\d+)?)")
 _DIVIDES = ("divide", "true_divide", "floor_divide")
 
@@ -100,7 +104,9 @@ class Measurement(np.ndarray):
         obj._apply_units(units)
         return obj
 
-    def _apply_units(self, spec):
+    @staticmethod
+    def _parse_units(spec):
+        """unit string -> (scale, dimensions, units as spelled) under the current code scales"""
         scale = np.double(1)
         dims, spelled = {}, {}
         for unit, power in _TOKEN.findall(spec or ""):
@@ -113,8 +119,22 @@ class Measurement(np.ndarray):
                 scale = scale * cs ** p
                 dims[dim] = dims.get(dim, 0) + dp * p
             spelled[unit] = spelled.get(unit, 0) + power
-        self.scale, self.units, self.original_units = scale, dims, spelled
-        np.multiply(self.view(np.ndarray), scale, out=self.view(np.ndarray))
+        return scale, dims, spelled
+
+    def _apply_units(self, spec):
+        # Object.__init__ parses the same five strings for every particle: remember the result per (string, code
+        # scales, unit table size); set_code_scale and new entries in unit_scale change the key
+        key = (spec, tuple(map(_FIRST, Measurement.code_scale.values())), len(Measurement.unit_scale))
+        hit = _PARSED.get(key)
+        if hit is None:
+            if len(_PARSED) > 4096:
+                _PARSED.clear()
+            hit = _PARSED[key] = Measurement._parse_units(spec)
+        scale, dims, spelled = hit
+        self.scale, self.units, self.original_units = scale, dict(dims), dict(spelled)
+        if scale != 1:
+            raw = self.view(np.ndarray)
+            np.multiply(raw, scale, out=raw)
 
     __scale__ = _apply_units  # the reference's name for it (physicl/__init__.py:141)
 
@@ -123,6 +143,9 @@ class Measurement(np.ndarray):
 
     def __array_finalize__(self, src):
         if src is None:
+            return
+        if type(src) is np.ndarray:  # a plain array viewed as a Measurement: dimensionless until told otherwise
+            self.scale, self.units, self.original_units = _ONE, {}, {}
             return
         self.scale = getattr(src, "scale", np.double(1))
         self.units = dict(getattr(src, "units", {}) or {})
