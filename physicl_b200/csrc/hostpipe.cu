@@ -173,11 +173,12 @@ static int host_compact_staged(pcl_ctx *ctx, const pcl_soa *host, float dt, cons
     pcl_hostpipe *hp = ctx->pipe;
     const bool wave = sp->mode & PCL_SCATTER_WAVELENGTH;
     if (wave) PCL_REQUIRE(ctx, host->e != nullptr, "wavelength law needs the e plane");
-    if (!hp->cnt_dev) {
-        PCL_CUDA(ctx, cudaMalloc(&hp->cnt_dev, PIPE_SLOTS * sizeof(uint64_t)));
+    if (!hp->out[PIPE_SLOTS - 1][8]) {  // the LAST buffer: an allocation that failed part-way is resumed, not skipped
+        if (!hp->cnt_dev) PCL_CUDA(ctx, cudaMalloc(&hp->cnt_dev, PIPE_SLOTS * sizeof(uint64_t)));
         if (!hp->cnt_pinned) PCL_CUDA(ctx, cudaMallocHost(&hp->cnt_pinned, PIPE_SLOTS * sizeof(uint64_t)));
         for (int s = 0; s < PIPE_SLOTS; ++s)
-            for (int q = 0; q < 9; ++q) PCL_CUDA(ctx, cudaMalloc(&hp->out[s][q], chunk * sizeof(float)));
+            for (int q = 0; q < 9; ++q)
+                if (!hp->out[s][q]) PCL_CUDA(ctx, cudaMalloc(&hp->out[s][q], chunk * sizeof(float)));
     }
     PCL_CUDA(ctx, cudaMemsetAsync(hp->tally_dev, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), hp->stream[0]));
     PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[0]));
