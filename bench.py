@@ -984,7 +984,14 @@ def main():
                     sub_args.steps = min(args.steps, 10)
                 if name.startswith("kinematics_1m"):
                     sub_args.steps = 1000  # BASELINE configs[0]: 1M particles x 1000 steps
-                out["sub"][name] = compact_sub(run_workload(name, sub_args, rank, world, local, clocks))
+                if world > 1:  # a rank that swallowed an error would leave the others waiting in a collective
+                    out["sub"][name] = compact_sub(run_workload(name, sub_args, rank, world, local, clocks))
+                    continue
+                try:  # a sub-result that fails (e.g. no memory left on a shared box) must not cost the headline line
+                    out["sub"][name] = compact_sub(run_workload(name, sub_args, rank, world, local, clocks))
+                except Exception as e:  # reported in the line, never hidden
+                    out["sub"][name] = {"error": repr(e)}
+                    torch.cuda.synchronize()
     out["clocks"] = clocks.summary() if rank == 0 else None
     if rank == 0 and world == 1 and not args.no_cpu and args.workload == "sweep_1b":
         out["cpu_baseline"] = cpu_baseline_block(args.steps, args.warmup)
