@@ -20,8 +20,9 @@ timestep / all timesteps in registers), wavelength_64m (configs[2]), gravity_256
   value      state resident in HBM; CUDA events around the K timesteps of each leg, queued behind a
              device-side gate (pcl_stream_gate) so that no host launch latency lies between the events;
              the photon legs are driven by sim.start() / sim.join() (the reference's entry point)
-  e2e        photon leg through the host-buffer C-ABI entry point with the particle planes in pinned HOST
-             memory between calls (H2D + kernel + D2H inside the timed region, host wall clock)
+  e2e        both legs through the host-buffer C-ABI entry points with the particle planes in pinned HOST
+             memory between calls (H2D + kernel + D2H inside the timed region, host wall clock), weighted
+             as in the resident job; each leg's own figure is in e2e.kinematics / e2e.photon_sphere
   roofline   dominant kernel (kinematics): algorithmic bytes / launch time
   tally_checksum   hash of the all-rank sums of every tally row of the timed photon leg and of an integer
              checksum of the kinematics state: identical at N = 1, 2, 4, 8 (results do not depend on sharding)
@@ -611,6 +612,56 @@ def _adopt_group(st, kind, planes, n, id_base):
     return g
 
 
+E2E_KIN_BLOCK = 16 * 2 ** 20  # particles of each rank's block the host-buffer kinematics leg steps (12 pinned planes)
+
+
+def leg_e2e_kinematics(args, ctx, world, n, m, k, host_chunk):
+    """Kinematics leg through pcl_kinematics_steps_host: r, v, a, dr planes in pinned HOST memory between calls, m timesteps
+    per round trip (36 B up + 36 B down per particle and round trip), the law of the resident leg (v += a dt; dr = v dt; r += dr)."""
+    import torch
+
+    from physicl_b200 import _capi
+
+    g = torch.Generator().manual_seed(1234)
+    host = {}
+    for nm in ("x", "y", "z"):
+        host[nm] = torch.empty(n, dtype=torch.float32, pin_memory=True).uniform_(-1e3, 1e3, generator=g)
+    for nm in ("vx", "vy", "vz"):
+        host[nm] = torch.empty(n, dtype=torch.float32, pin_memory=True).normal_(0.0, 10.0, generator=g)
+    for nm, val in (("ax", 0.0), ("ay", 0.0), ("az", -9.81), ("dx", 0.0), ("dy", 0.0), ("dz", 0.0)):
+        host[nm] = torch.full((n,), val, dtype=torch.float32).pin_memory()
+    soa = _capi.Soa()
+    soa.n = n
+    for nm, t in host.items():
+        setattr(soa, nm, t.data_ptr())
+
+    def call(steps):
+        ctx.call("pcl_kinematics_steps_host", C.byref(soa), C.c_float(DT), 1, None, C.c_uint32(steps), C.c_uint64(host_chunk))
+
+    s = 0
+    while s < args.warmup:
+        run = min(m, args.warmup - s)
+        call(run)
+        s += run
+    trips = 0
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    while s < args.warmup + k:
+        run = min(m, args.warmup + k - s)
+        call(run)
+        s += run
+        trips += 1
+    wall = time.perf_counter() - t0
+    barrier_sync(world)
+    wall = max_over_ranks(wall, world)
+    up = down = 36 * n * trips
+    return {"value": float(n) * world * k / wall, "unit": "particle-steps/s", "particles_per_gpu": n, "steps": k,
+            "timesteps_per_round_trip": m, "h2d_bytes_per_step": up // k, "d2h_bytes_per_step": down // k,
+            "pcie_per_gpu": {"h2d_GBps": up / wall / 1e9, "d2h_GBps": down / wall / 1e9},
+            "path": "pcl_kinematics_steps_host: pinned host planes r, v, a (36 B up) -> 1 Mi-particle chunks -> one launch advancing "
+                    "the timesteps of the round trip in registers -> r, v, dr back (36 B down), 4 streams"}
+
+
 def leg_e2e(args, rank, world, local, n, id_base):
     """Photon leg through the host-buffer entry points: the planes (r, v, id) live in pinned HOST memory between calls.
     Primary: pcl_photon_steps_host_compact, m = 8 timesteps per host round trip (what Simulation.run needs when no host step
@@ -649,6 +700,8 @@ def leg_e2e(args, rank, world, local, n, id_base):
         state["n"] = n_out.value
         state["live"] += int(rows[:m, _capi.T_LIVE_IN].sum())
 
+    wall_of = {}
+
     def measure(m, k):
         state = reset()
         s = 0
@@ -666,6 +719,7 @@ def leg_e2e(args, rank, world, local, n, id_base):
         wall = time.perf_counter() - t0
         barrier_sync(world)
         wall = max_over_ranks(wall, world)
+        wall_of[m] = wall
         # PCIe rate of this rank's link, both directions at once (the measured bidirectional ceiling is in profiles/bench_r1/pcie_peak.txt)
         link = {"h2d_GBps": state["up"] / wall / 1e9, "d2h_GBps": state["down"] / wall / 1e9,
                 # what the host's memory system sustains for all ranks' DMA together (reads + writes of pinned memory): this, not
@@ -676,8 +730,23 @@ def leg_e2e(args, rank, world, local, n, id_base):
     v8, up8, down8, link8 = measure(8, args.steps)
     k1 = max(3, min(args.steps, 6))
     v1, up1, down1, link1 = measure(1, k1)
-    return {"value": v8, "unit": "particle-steps/s", "h2d_bytes_per_step": up8, "d2h_bytes_per_step": down8, "steps": args.steps,
-            "pcie_per_gpu": link8,
+    del host
+    kin8 = leg_e2e_kinematics(args, ctx, world, min(n, E2E_KIN_BLOCK), 8, args.steps, host_chunk)
+    kin1 = leg_e2e_kinematics(args, ctx, world, min(n, E2E_KIN_BLOCK), 1, k1, host_chunk)
+
+    def both(r_kin, r_ph, live_frac):
+        # whole job through host buffers: equal particle counts in both legs, as in the resident job; per particle and
+        # timestep the kinematics leg does 1 unit, the photon leg `live_frac` units: total units / total time
+        return (1.0 + live_frac) / (1.0 / r_kin + live_frac / r_ph)
+
+    live8 = v8 * wall_of[8] / (float(n) * world * args.steps)
+    live1 = v1 * wall_of[1] / (float(n) * world * k1)
+    return {"value": both(kin8["value"], v8, live8), "unit": "particle-steps/s",
+            "h2d_bytes_per_step": up8 + kin8["h2d_bytes_per_step"], "d2h_bytes_per_step": down8 + kin8["d2h_bytes_per_step"],
+            "steps": args.steps, "legs": "kinematics + photon sphere, weighted as in the resident job (equal particle counts; the "
+                                         "photon leg counts live photon-steps): (1 + f) / (1 / r_kin + f / r_photon), f = %.4f" % live8,
+            "photon_sphere": {"value": v8, "h2d_bytes_per_step": up8, "d2h_bytes_per_step": down8},
+            "pcie_per_gpu": link8, "kinematics": kin8,
             "timesteps_per_round_trip": 8, "photons_per_gpu": n,
             "timer": "host wall clock around the synchronous C-ABI calls, max over ranks",
             "path": "pcl_photon_steps_host_compact: pinned host SoA planes (r, v, id) -> 1 Mi-photon chunks H2D -> ONE fused launch "
@@ -686,7 +755,10 @@ def leg_e2e(args, rank, world, local, n, id_base):
                     "device steps",
             "sample": "the first %d photons of each rank's block (the path streams 1 Mi-photon chunks: its throughput does not depend "
                       "on the block size)" % n,
-            "one_timestep_per_round_trip": {"value": v1, "h2d_bytes_per_step": up1, "d2h_bytes_per_step": down1, "steps": k1,
+            "one_timestep_per_round_trip": {"value": both(kin1["value"], v1, live1), "photon_sphere": {"value": v1},
+                                            "kinematics": kin1,
+                                            "h2d_bytes_per_step": up1 + kin1["h2d_bytes_per_step"],
+                                            "d2h_bytes_per_step": down1 + kin1["d2h_bytes_per_step"], "steps": k1,
                                             "pcie_per_gpu": link1,
                                             "path": "pcl_photon_step_host_compact: the same, planes back in host memory after EVERY timestep "
                                                     "(28 B up + 28 B down per photon-step over PCIe)"}}

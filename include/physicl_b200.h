@@ -265,6 +265,11 @@ int pcl_photon_steps_host_compact(pcl_ctx *ctx, const pcl_soa *host, float dt,
                                   const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2,
                                   const pcl_planes *planes, int64_t *tally_rows_host, uint64_t chunk,
                                   uint32_t nsteps, uint64_t *n_out_host);
+/* NewtonianKinematicsStep (physicl/newton.py:14-16; with accel the v += a dt law of pcl_kinematics) over HOST planes,
+ * nsteps timesteps per round trip: r, v [, a] go up, r [, v with accel] [, dr when the host view has dr planes] come
+ * back; same chunked pipeline as the photon entry points.  Bit-identical to pcl_kinematics_steps on resident planes. */
+int pcl_kinematics_steps_host(pcl_ctx *ctx, const pcl_soa *host, float dt, int accel, const float *a_uniform,
+                              uint32_t nsteps, uint64_t chunk);
 int pcl_host_register(pcl_ctx *ctx, void *ptr, uint64_t bytes);
 int pcl_host_unregister(pcl_ctx *ctx, void *ptr);
 

@@ -86,6 +86,7 @@ _PROTOS = {
     "pcl_stream_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "pcl_kinematics": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_int, _f32p]),
     "pcl_kinematics_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_int, _f32p, C.c_uint32]),
+    "pcl_kinematics_steps_host": (C.c_int, [C.c_void_p, C.POINTER(Soa), C.c_float, C.c_int, _f32p, C.c_uint32, C.c_uint64]),
     "pcl_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.POINTER(ScatterParams), C.POINTER(Rng), C.c_void_p, C.c_void_p]),
     "pcl_escape": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.c_void_p]),
     "pcl_photon_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Soa), C.c_float, C.POINTER(ScatterParams), C.POINTER(Rng), C.c_float, C.POINTER(Planes), C.c_void_p]),

@@ -14,6 +14,9 @@ int pcl_photon_step_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, const 
                          const pcl_scatter_params *sp, const pcl_rng *rng, float escape_r2, const pcl_planes *planes,
                          int64_t *tally_row, uint64_t *n_out, uint32_t nsteps, bool keep_count);
 
+int pcl_kinematics_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, int accel, const float *a_uniform,
+                        uint32_t nsteps);
+
 #define PIPE_SLOTS 4
 #define PIPE_PLANES 11  // x y z vx vy vz e id nscat + u_theta u_phi (u_rand shares a slot below)
 
@@ -342,5 +345,57 @@ extern "C" int pcl_photon_step_host_compact(pcl_ctx *ctx, const pcl_soa *host, f
     PCL_CUDA(ctx, cudaMemcpy(hp->cnt_pinned, hp->total_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     memcpy(tally_row_host, hp->tally_pinned, PCL_TALLY_COLS * sizeof(int64_t));
     *n_out_host = hp->cnt_pinned[0];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kinematics over HOST planes: the same chunked pipeline for NewtonianKinematicsStep (physicl/newton.py:14-16; with
+// accel, the constant-acceleration law of BASELINE configs[0]).  A chunk goes up once (r, v [, a]), is advanced nsteps
+// timesteps in registers by one launch (pcl_kinematics_steps) and comes back (r [, v when accel] [, dr when the host
+// has dr planes]); a planes are inputs only.  Bytes over PCIe per particle and round trip with a and dr planes:
+// 36 B up + 36 B down.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pcl_kinematics_steps_host(pcl_ctx *ctx, const pcl_soa *host, float dt, int accel, const float *a_uniform,
+                                         uint32_t nsteps, uint64_t chunk) {
+    PCL_ENTER(ctx);
+    PCL_REQUIRE(ctx, host != nullptr, "null particle view");
+    PCL_REQUIRE(ctx, host->x && host->y && host->z && host->vx && host->vy && host->vz, "r and v planes are required");
+    PCL_REQUIRE(ctx, host->n_dev == nullptr, "host planes carry their slot count in n");
+    const bool has_a = accel && host->ax != nullptr, has_d = host->dx != nullptr;
+    if (has_a) PCL_REQUIRE(ctx, host->ay && host->az, "a planes must come as a triple");
+    if (has_d) PCL_REQUIRE(ctx, host->dy && host->dz, "dr planes must come as a triple");
+    if (accel && !has_a) PCL_REQUIRE(ctx, a_uniform != nullptr, "accel requested without a planes or a_uniform");
+    if (nsteps == 0 || host->n == 0) return 0;
+    if (chunk == 0) chunk = 1u << 20;
+    chunk = (chunk + 3) & ~(uint64_t)3;
+    int rc = pipe_prepare(ctx, chunk);
+    if (rc) return rc;
+    pcl_hostpipe *hp = ctx->pipe;
+    float *hplane[12] = {host->x, host->y, host->z, host->vx, host->vy, host->vz, host->ax, host->ay, host->az,
+                         host->dx, host->dy, host->dz};
+    const uint64_t nchunks = (host->n + chunk - 1) / chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % PIPE_SLOTS);
+        cudaStream_t st = hp->stream[s];  // chunk c + PIPE_SLOTS reuses these buffers: stream order keeps it behind c's D2H
+        const uint64_t off = c * chunk;
+        const uint64_t m = (host->n - off < chunk) ? host->n - off : chunk;
+        const size_t bytes = m * sizeof(float);
+        float **b = hp->buf[s];
+        for (int q = 0; q < (has_a ? 9 : 6); ++q)
+            PCL_CUDA(ctx, cudaMemcpyAsync(b[q], hplane[q] + off, bytes, cudaMemcpyHostToDevice, st));
+        pcl_soa d;
+        memset(&d, 0, sizeof(d));
+        d.n = m;
+        d.x = b[0]; d.y = b[1]; d.z = b[2]; d.vx = b[3]; d.vy = b[4]; d.vz = b[5];
+        if (has_a) { d.ax = b[6]; d.ay = b[7]; d.az = b[8]; }
+        if (has_d) { d.dx = b[9]; d.dy = b[10]; d.dz = b[11]; }
+        rc = pcl_kinematics_impl(ctx, st, &d, dt, accel, a_uniform, nsteps);
+        if (rc) return rc;
+        for (int q = 0; q < 12; ++q) {
+            const bool back = q < 3 || (q < 6 && accel) || (q >= 9 && has_d);
+            if (back) PCL_CUDA(ctx, cudaMemcpyAsync(hplane[q] + off, b[q], bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int s = 0; s < PIPE_SLOTS; ++s) PCL_CUDA(ctx, cudaStreamSynchronize(hp->stream[s]));
     return 0;
 }

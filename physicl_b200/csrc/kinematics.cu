@@ -163,6 +163,12 @@ static int kin_dispatch(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float d
     }
 }
 
+// for hostpipe.cu: the same dispatch on a stream of the host pipeline
+int pcl_kinematics_impl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa *p, float dt, int accel, const float *a_uniform,
+                        uint32_t nsteps) {
+    return kin_dispatch(ctx, st, p, dt, accel, a_uniform, nsteps);
+}
+
 extern "C" int pcl_kinematics(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, float dt, int accel,
                               const float *a_uniform) {
     PCL_ENTER(ctx);

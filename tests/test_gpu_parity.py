@@ -69,6 +69,45 @@ def test_kinematics_unaligned_view_takes_scalar_path(ctx):
         assert u.same_bits(g.download(nm)[1:], host[nm]), nm
 
 
+@pytest.mark.parametrize("accel,with_dr,pinned", [(0, True, True), (1, True, True), (1, False, False), (2, True, False), (0, False, True)])
+def test_kinematics_host_buffer_steps_equal_the_twin(ctx, accel, with_dr, pinned):
+    """pcl_kinematics_steps_host (planes in HOST memory, chunked H2D -> k timesteps in registers -> D2H) against the
+    binary32 twin, bit for bit; planes that are inputs only (a; v without accel) keep their bits; several chunks, a
+    ragged last one, and guard bands around every host plane."""
+    import torch
+
+    n, pad, chunk = 300_007, 16, 65_536
+    rng = np.random.default_rng(11 + accel)
+    names = ["x", "y", "z", "vx", "vy", "vz"] + (["ax", "ay", "az"] if accel == 1 else []) + (["dx", "dy", "dz"] if with_dr else [])
+    full = {}
+    for nm in names:
+        t = torch.full((n + 2 * pad,), 12345.0, dtype=torch.float32)
+        if pinned:
+            t = t.pin_memory()
+        scale = 1e3 if nm in "xyz" else (10.0 if nm.startswith("v") else (3.0 if nm.startswith("a") else 0.0))
+        t[pad:pad + n] = torch.from_numpy((rng.normal(0, 1, n) * scale).astype(np.float32))
+        full[nm] = t
+    host = {nm: t[pad:pad + n].numpy().copy() for nm, t in full.items()}
+    from physicl_b200 import _capi
+
+    soa = _capi.Soa()
+    soa.n = n
+    for nm, t in full.items():
+        setattr(soa, nm, t.data_ptr() + 4 * pad)
+    au = np.array([0.5, 0.0, -9.81], np.float32)
+    pau = au.ctypes.data_as(C.POINTER(C.c_float)) if accel == 2 else None
+    done = 0
+    for k in (3, 1, 8):
+        ctx.call("pcl_kinematics_steps_host", C.byref(soa), C.c_float(1e-3), int(accel != 0), pau, C.c_uint32(k), C.c_uint64(chunk))
+        for _ in range(k):
+            oracle.kinematics_f32(host, 1e-3, accel, au if accel == 2 else None)
+        done += k
+    for nm, t in full.items():
+        got = t.numpy()
+        assert (got[:pad] == 12345.0).all() and (got[pad + n:] == 12345.0).all(), nm
+        assert _u().same_bits(got[pad:pad + n], host[nm]), nm
+
+
 @pytest.mark.parametrize("accel", [0, 1, 2])
 def test_kinematics_timesteps_in_registers_equal_single_steps(ctx, accel):
     """pcl_kinematics_steps (k timesteps per HBM round trip) == k launches of pcl_kinematics == the twin."""
