@@ -9,7 +9,7 @@
 // Ranks inside a tile come from 4-bit live masks + a shuffle scan, survivors are staged in shared
 // memory and written as contiguous, 16-byte vectorised runs; the order of survivors is preserved (results
 // never depend on block scheduling).  16 Mi slots of (r, v) + generated ids: 173 us all live (0.83 of the HBM copy
-// bandwidth in real traffic), 133 us with 17 % live (0.63); the first version took 214 / 158 us.  A single-launch form
+// bandwidth in real traffic), 123 us with 17 % live (0.68; five resident CTAs per SM); the first version took 214 / 158 us.  A single-launch form
 // with a chained scan (tickets + decoupled look-back) was built and measured: 332 / 279 us -- with 1024-slot tiles and
 // four resident CTAs per SM the look-back latency sits on every tile's critical path -- and dropped.
 #include "pcl_common.cuh"
@@ -150,7 +150,7 @@ __device__ __forceinline__ float4 pcl_ld4_guarded(const float *p, uint64_t i, ui
 }
 
 template <bool EXT>
-__global__ void __launch_bounds__(PCL_BLOCK)
+__global__ void __launch_bounds__(PCL_BLOCK, EXT ? 3 : 5)
 pcl_k_compact(pcl_soa s, pcl_soa d, const uint32_t *offsets, int vec_ok) {
     constexpr int NP = EXT ? 15 : 9;
     __shared__ uint32_t s_w[PCL_WARPS];
