@@ -482,7 +482,8 @@ def photon_sim(n, rank, local, id_base=None):
     sim.add_particles(r, v, E=None, id_base=rank * n if id_base is None else id_base)
     sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(DT)))
     sim.add_step(1, phys.newton.NewtonianKinematicsStep())
-    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+    # PCL_BENCH_SFU=1 (tuning aid, not the default): directions from MUFU sin / cos instead of the reproducible table
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3), sfu_trig=os.environ.get("PCL_BENCH_SFU") == "1"))
     esc = phys.light.EscapeSphereStep(R_ESCAPE)
     sim.add_step(3, esc)
     sign = phys.light.ScatterSignMeasureStep(None, True)
@@ -954,7 +955,8 @@ def bench_wavelength(args, rank, world, local, clocks):
     A, nd, dt = 5.1e-31 * (532e-9) ** 4, 2.5e25, 1e-5
     sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(dt)))
     sim.add_step(1, phys.newton.NewtonianKinematicsStep())
-    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True))
+    sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(A), n=np.double(nd), wavelength_dep_scattering=True,
+                                                    sfu_trig=os.environ.get("PCL_BENCH_SFU") == "1"))
     sign = phys.light.ScatterSignMeasureStep(None, True)
     sim.add_step(3, sign)
     sim.device_store().group("photon").e0 = E0

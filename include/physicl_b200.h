@@ -79,7 +79,11 @@ typedef struct pcl_pingpong {
  * (physicl/light.py:303-315, :146-158, :239-249). */
 enum {
     PCL_SCATTER_WAVELENGTH = 1, /* pcoll *= (h c / E)^-4   (light.py:300-301)            */
-    PCL_SCATTER_DELETE = 2      /* scattered photons are removed (light.py:146-158)      */
+    PCL_SCATTER_DELETE = 2,     /* scattered photons are removed (light.py:146-158)      */
+    PCL_SCATTER_SFU = 4         /* new directions from the SFU (MUFU.SIN / MUFU.COS, sin.approx / cos.approx) instead of
+                                 * the table + addition theorem: |error| ~ 5e-7, NOT reproducible on a CPU, so results
+                                 * agree with the default in law (and in the first timestep's decisions), not bit for
+                                 * bit.  Opt-in; fused Philox kernels on 16-byte aligned planes only. */
 };
 typedef struct pcl_scatter_params {
     float k;       /* A*n, or A*n*(E0/(h c))^4 with PCL_SCATTER_WAVELENGTH (folded in f64 on host) */

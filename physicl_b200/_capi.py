@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PHYSICL_B200_LIB") or os.path.join(_HERE, "libphysicl
 MAX_PLANES = 8
 TALLY_COLS = 16
 T_ALIVE, T_XP, T_YP, T_ZP, T_SCATTERED, T_ABSORBED, T_ESCAPED, T_LIVE_IN, T_PLANE0 = range(9)
-SCATTER_WAVELENGTH, SCATTER_DELETE = 1, 2
+SCATTER_WAVELENGTH, SCATTER_DELETE, SCATTER_SFU = 1, 2, 4
 
 # Thread-level SASS instructions of the shipped fused photon kernels, from ncu (profiles/r2/ncu_full_photon_multi_v3.csv,
 # ncu_full_photon_wave_inplace_v3.csv; static loop counts by scripts/sass_loop.py agree): per photon-step inside the timestep

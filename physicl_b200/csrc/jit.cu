@@ -251,6 +251,7 @@ extern "C" int pcl_photon_steps_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kern
     PCL_REQUIRE(ctx, p->n < (1ull << 32), "a shard holds fewer than 2^32 slots");
     PCL_REQUIRE(ctx, (p->id_base & 0xffffffffull) + p->n <= (1ull << 32), "the global ids of a shard must not cross a multiple of 2^32");
     if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
+    PCL_REQUIRE(ctx, !(sp->mode & PCL_SCATTER_SFU), "PCL_SCATTER_SFU applies to the pre-compiled fused photon steps only");
     PCL_REQUIRE(ctx, nsteps == 1 || rng->u_rand == nullptr, "multi-step runs draw from Philox; injected uniforms are per step");
     cudaStream_t st = (cudaStream_t)stream;
     PCL_CUDA(ctx, cudaMemsetAsync(tally_table, 0, (size_t)nsteps * PCL_TALLY_COLS * sizeof(int64_t), st));
@@ -283,6 +284,7 @@ extern "C" int pcl_scatter_jit(pcl_ctx *ctx, uintptr_t stream, pcl_jit_kernel *k
     PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "stand-alone scatter reads the dr planes");
     PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
     if (sp->mode & PCL_SCATTER_WAVELENGTH) PCL_REQUIRE(ctx, p->e != nullptr, "wavelength law needs the e plane");
+    PCL_REQUIRE(ctx, !(sp->mode & PCL_SCATTER_SFU), "PCL_SCATTER_SFU applies to the pre-compiled fused photon steps only");
     if (p->n == 0) return 0;
     StepK K;
     int rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr, p->id_base);

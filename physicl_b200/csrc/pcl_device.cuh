@@ -128,11 +128,21 @@ __device__ __forceinline__ void pcl_sincos_tab2(const unsigned char *tab, uint32
     c = fma2(ca, cb, sub2(pk(0.f, 0.f), mul2(sa, sb)));
 }
 
+// PCL_SCATTER_SFU: sin and cos of two angles (radians) on the special-function unit (MUFU.SIN / MUFU.COS after the
+// range-reduction multiply): 2^-20.9 absolute error on [-pi, pi], a little more up to 2 pi.
+__device__ __forceinline__ void pcl_sincos_sfu2(f32x2 ang, f32x2 &s, f32x2 &c) {
+    float a0, a1;
+    upk(ang, a0, a1);
+    s = pk(__sinf(a0), __sinf(a1));
+    c = pk(__cosf(a0), __cosf(a1));
+}
+
 // One photon's random numbers for one timestep, in the form the step body consumes them.
 struct pcl_draw3 {
     float ur;         // U[0,1) of the collision test (24 bits)
     uint32_t at, ap;  // byte offsets of the table entries below theta and below phi
     float bt, bp;     // remainders: theta = entry angle + bt (bt < 2 pi/256), phi = entry angle + bp (bp < pi/256)
+    float tf, pf;     // RAW draws only: the whole 24-bit theta field and 16-bit phi field as floats (PCL_SCATTER_SFU)
 };
 
 // from one Philox2x32 block (w0, w1):  ur = w0[31:8];  theta = 2 pi * w1[31:8] / 2^24;  phi = pi * (w1[7:0] : w0[7:0]) / 2^16.
@@ -140,6 +150,8 @@ struct pcl_draw3 {
 // power-of-two-exact scalings to two photons per instruction (and folds 2^-24 into 1/k).  pcl_draw_finish scales one draw.
 #define PCL_BT_SCALE (PCL_TWO_PI_256 * 0x1p-16f)
 #define PCL_BP_SCALE (PCL_PI_256 * 0x1p-8f)
+#define PCL_SFU_T_SCALE (PCL_TWO_PI_256 * 0x1p-16f) /* 2 pi / 2^24: theta from the whole 24-bit field */
+#define PCL_SFU_P_SCALE (PCL_PI_256 * 0x1p-8f)      /*   pi / 2^16: phi from the whole 16-bit field   */
 __device__ __forceinline__ pcl_draw3 pcl_draw_bits_raw(uint32_t w0, uint32_t w1) {
     pcl_draw3 d;
     d.ur = (float)(w0 >> 8);
@@ -147,6 +159,8 @@ __device__ __forceinline__ pcl_draw3 pcl_draw_bits_raw(uint32_t w0, uint32_t w1)
     d.bt = (float)((w1 >> 8) & 0xffffu);
     d.ap = (w1 & 0xffu) << 2;  // k8 = w1[7:0], entry k8
     d.bp = (float)(w0 & 0xffu);
+    d.tf = (float)(w1 >> 8);                                // dead code unless the SFU form is instantiated
+    d.pf = (float)(((w1 & 0xffu) << 8) | (w0 & 0xffu));
     return d;
 }
 __device__ __forceinline__ pcl_draw3 pcl_draw_finish(pcl_draw3 d) {
@@ -167,6 +181,7 @@ __device__ __forceinline__ pcl_draw3 pcl_draw_floats(float ut, float up, float u
     const float tp = up * 256.0f, kp = floorf(tp);
     d.ap = ((uint32_t)(int)kp & 0xffu) << 2;
     d.bp = (tp - kp) * PCL_PI_256;
+    d.tf = d.pf = 0.f;
     return d;
 }
 

@@ -12,6 +12,7 @@ struct StepK {
     float r2_escape;  // NaN: no sphere (r2 >= NaN is false)
     uint32_t rk[10];  // Philox2x32 round keys key + r*W (key = fold of seed, high id word, stream)
     uint32_t step;
+    uint32_t sfu;     // PCL_SCATTER_SFU: directions from MUFU sin / cos (fused Philox kernels)
     uint32_t nplanes;
     uint32_t axis[PCL_MAX_PLANES];
     float loc[PCL_MAX_PLANES];
@@ -304,7 +305,7 @@ __device__ __forceinline__ void pcl_tally_photon(const StepK &K, bool live, bool
     }
 }
 
-template <bool WAVE, bool DEL, bool PL, bool RAW>
+template <bool WAVE, bool DEL, bool PL, bool RAW, bool SFU = false>
 __device__ __forceinline__ void pcl_photon_two(const StepK &K, const unsigned char *tab, float &xA, float &xB, float &yA, float &yB,
                                                float &zA, float &zB, float &vxA, float &vxB, float &vyA, float &vyB, float &vzA,
                                                float &vzB, float eA, float eB, const pcl_draw3 &dA, const pcl_draw3 &dB,
@@ -332,13 +333,19 @@ __device__ __forceinline__ void pcl_photon_two(const StepK &K, const unsigned ch
     hitB = liveB && (lB >= qB);
     if (!DEL) {
         f32x2 st, ct, sp, cp;
-        f32x2 bt = pk(dA.bt, dB.bt), bp = pk(dA.bp, dB.bp);
-        if (RAW) {
-            bt = mul2(bt, pk(PCL_BT_SCALE, PCL_BT_SCALE));
-            bp = mul2(bp, pk(PCL_BP_SCALE, PCL_BP_SCALE));
+        if (SFU) {  // theta = 2 pi m / 2^24, phi = pi m / 2^16 straight from the integer fields, then MUFU
+            static_assert(!SFU || RAW, "the SFU form consumes raw Philox fields");
+            pcl_sincos_sfu2(mul2(pk(dA.tf, dB.tf), pk(PCL_SFU_T_SCALE, PCL_SFU_T_SCALE)), st, ct);
+            pcl_sincos_sfu2(mul2(pk(dA.pf, dB.pf), pk(PCL_SFU_P_SCALE, PCL_SFU_P_SCALE)), sp, cp);
+        } else {
+            f32x2 bt = pk(dA.bt, dB.bt), bp = pk(dA.bp, dB.bp);
+            if (RAW) {
+                bt = mul2(bt, pk(PCL_BT_SCALE, PCL_BT_SCALE));
+                bp = mul2(bp, pk(PCL_BP_SCALE, PCL_BP_SCALE));
+            }
+            pcl_sincos_tab2(tab, dA.at, dB.at, bt, st, ct);  // theta = 2 pi u
+            pcl_sincos_tab2(tab, dA.ap, dB.ap, bp, sp, cp);  // phi   =   pi u
         }
-        pcl_sincos_tab2(tab, dA.at, dB.at, bt, st, ct);  // theta = 2 pi u
-        pcl_sincos_tab2(tab, dA.ap, dB.ap, bp, sp, cp);  // phi   =   pi u
         const f32x2 c2 = pk(K.c, K.c);
         const f32x2 cs = mul2(c2, st);
         float nA, nB;

@@ -212,7 +212,7 @@ pcl_k_photon_step_tail(pcl_soa p, StepK K, int64_t *row, int aligned) {
 #ifndef PCL_MULTI_MINB_INPLACE
 #define PCL_MULTI_MINB_INPLACE PCL_PHOTON_MINB
 #endif
-template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT>
+template <bool WAVE, bool DEL, bool INJ, bool PL, bool COMPACT, bool SFU = false>
 __global__ void __launch_bounds__(PCL_BLOCK, COMPACT ? PCL_MULTI_MINB_COMPACT : PCL_MULTI_MINB_INPLACE)
 pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long long *n_out, uint32_t nsteps, int prefetch) {
     constexpr int NST = COMPACT ? 9 : 1;  // staged planes: x y z vx vy vz id nscat e
@@ -324,7 +324,7 @@ pcl_k_photon_multi(pcl_soa s, pcl_soa d, StepK K, int64_t *rows, unsigned long l
             bool hit[4];
 #pragma unroll
             for (int l = 0; l < 4; l += 2)  // photons (0,1) and (2,3) as pairs: packed FP32
-                pcl_photon_two<WAVE, DEL, PL, !INJ>(K, s_tab, pcl_f4(x, l), pcl_f4(x, l + 1), pcl_f4(y, l), pcl_f4(y, l + 1), pcl_f4(z, l),
+                pcl_photon_two<WAVE, DEL, PL, !INJ, SFU>(K, s_tab, pcl_f4(x, l), pcl_f4(x, l + 1), pcl_f4(y, l), pcl_f4(y, l + 1), pcl_f4(z, l),
                                               pcl_f4(z, l + 1), pcl_f4(vx, l), pcl_f4(vx, l + 1), pcl_f4(vy, l), pcl_f4(vy, l + 1),
                                               pcl_f4(vz, l), pcl_f4(vz, l + 1), pcl_f4(e, l), pcl_f4(e, l + 1), dr[l], dr[l + 1], t,
                                               hit[l], hit[l + 1]);
@@ -588,6 +588,7 @@ int pcl_fill_stepk(pcl_ctx *ctx, StepK &K, float dt, const pcl_scatter_params *s
             K.kinv = nanf("");
         }
         K.kinv24 = ldexpf(K.kinv, -24);
+        K.sfu = (sp->mode & PCL_SCATTER_SFU) ? 1u : 0u;
     }
     K.r2_escape = escape_r2 > 0.f ? escape_r2 : nanf("");
     if (rng) {
@@ -648,6 +649,7 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
                          pcl_aligned16(p.vy) && pcl_aligned16(p.vz) && pcl_aligned16(p.e) && pcl_aligned16(p.id) &&
                          pcl_aligned16(p.nscat) && pcl_aligned16(K.u_theta) && pcl_aligned16(K.u_phi) &&
                          pcl_aligned16(K.u_rand);
+    if (K.sfu && !DEL) PCL_REQUIRE(ctx, aligned && !INJ, "PCL_SCATTER_SFU needs 16-byte aligned planes and Philox draws");
     if (dst) {  // retire-and-compact form: one kernel handles every slot, tail included
         PCL_REQUIRE(ctx, aligned, "the compacting step needs 16-byte aligned planes");
         if (!keep_count) PCL_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(uint64_t), st));
@@ -655,6 +657,9 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         const int pf = multi_prefetch() && !INJ;
         const size_t smem = pf ? (size_t)(6 + (p.id ? 1 : 0) + (WAVE ? 1 : 0) + (p.nscat ? 1 : 0)) * PCL_BLOCK * sizeof(float4) : 0;
         auto kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, true>;
+        if constexpr (!INJ && !DEL) {
+            if (K.sfu) kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, true, true>;
+        }
         if (pf) PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, PCL_BLOCK, smem, st>>>(p, *dst, K, row, (unsigned long long *)n_out, nsteps, pf);
         PCL_LAUNCHED(ctx);
@@ -668,12 +673,15 @@ static int launch_photon_pl(pcl_ctx *ctx, cudaStream_t st, const pcl_soa &p, con
         const char *e = getenv("PCL_PHOTON_SINGLE_MULTI");
         single_multi = e ? atoi(e) : 1;
     }
-    if (nsteps > 1 || (single_multi && aligned && !INJ)) {  // several timesteps per HBM round trip, in place
+    if (nsteps > 1 || ((single_multi || (K.sfu && !DEL)) && aligned && !INJ)) {  // several timesteps per HBM round trip, in place
         PCL_REQUIRE(ctx, aligned, "multi-step launches need 16-byte aligned planes");
         unsigned grid = pcl_stream_grid(ctx, (p.n + 3) / 4, PCL_BLOCK, 8);
         const int pf = multi_prefetch() && !INJ;
         const size_t smem = pf ? (size_t)(6 + (p.id ? 1 : 0) + (WAVE ? 1 : 0) + (p.nscat ? 1 : 0)) * PCL_BLOCK * sizeof(float4) : 0;
         auto kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, false>;
+        if constexpr (!INJ && !DEL) {
+            if (K.sfu) kern = pcl_k_photon_multi<WAVE, DEL, INJ, PL, false, true>;
+        }
         if (pf) PCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, PCL_BLOCK, smem, st>>>(p, p, K, row, nullptr, nsteps, pf);
         PCL_LAUNCHED(ctx);
@@ -864,6 +872,7 @@ extern "C" int pcl_scatter(pcl_ctx *ctx, uintptr_t stream, const pcl_soa *p, con
     if (rc) return rc;
     PCL_REQUIRE(ctx, p->dx && p->dy && p->dz, "stand-alone scatter reads the dr planes");
     PCL_REQUIRE(ctx, p->n_dev == nullptr, "this step needs the exact slot count on the host (n_dev must be null)");
+    PCL_REQUIRE(ctx, !(sp->mode & PCL_SCATTER_SFU), "PCL_SCATTER_SFU applies to the fused photon steps only");
     if (p->n == 0) return 0;
     StepK K;
     rc = pcl_fill_stepk(ctx, K, 0.f, sp, rng, 0.f, nullptr, p->id_base);

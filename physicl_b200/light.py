@@ -181,6 +181,8 @@ class _ScatterBase(physicl.Step):
             # pcoll = A n |dr| (h c / E)^-4 (light.py:300-301) = [A n (E0 / (h c))^4] |dr| (E/E0)^4
             k = k * (group.e0 / (float(h) * float(c))) ** 4
             mode |= _capi.SCATTER_WAVELENGTH
+        if getattr(self, "sfu_trig", False) and not (mode & _capi.SCATTER_DELETE):
+            mode |= _capi.SCATTER_SFU
         return _capi.ScatterParams(k=k, c=float(c), mode=mode)
 
     def varn_params(self, group):
@@ -259,6 +261,11 @@ class ScatterIsotropicStep(_ScatterBase):
     step's ``n`` (light.py:287 swaps the two constants), so the step's ``A`` does not enter unless
     ``variable_n_apply_A=True`` is passed (SURVEY.md appendix A #5).
 
+    ``sfu_trig=True`` (new, opt-in): the sines and cosines of a new direction come from the GPU's special-function unit
+    (MUFU.SIN / MUFU.COS, |error| ~ 5e-7) instead of the table + addition theorem the CPU twin reproduces bit for bit: 7 %
+    fewer instructions in the fused photon loop; results then agree with the default in law (same decisions in the first
+    timestep, same distributions), not bit for bit.  Fused pipelines with in-kernel draws only.
+
     Note the direction law is the reference's: theta ~ U[0, 2 pi) polar, phi ~ U[0, pi) azimuth
     (light.py:285, :309-311), which is not uniform on the sphere (SURVEY.md appendix A #11)."""
 
@@ -269,6 +276,7 @@ class ScatterIsotropicStep(_ScatterBase):
         self.variable_n = kwargs.get("variable_n", False)
         self.variable_n_fn = kwargs.get("variable_n_fn", None)
         self.variable_n_apply_A = kwargs.get("variable_n_apply_A", False)
+        self.sfu_trig = bool(kwargs.get("sfu_trig", False))
         self._jit = {}  # ctx id -> jit.Module
         if self.variable_n:
             from . import jit

@@ -732,6 +732,90 @@ def test_compacting_step_matches_twin_by_id(ctx, mode, n):
             assert u.same_bits(snap[nm], host[nm]), (step, nm)
 
 
+@pytest.mark.parametrize("wave", [0, 1])
+def test_sfu_directions_same_first_step_decisions_and_same_law(ctx, wave):
+    """PCL_SCATTER_SFU (opt-in): new directions from MUFU.SIN / MUFU.COS instead of the reproducible table.  The first
+    timestep's decisions do not depend on the direction arithmetic, so tally rows, scattered sets and positions equal
+    the default form's; the new velocities agree to 2e-6 c (both approximate the same angles) and |v| = c to 1e-5;
+    over more timesteps the two forms agree in law: scattered counts within 5 sigma, v_z / c arcsine-distributed (KS)."""
+    from scipy import stats
+
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 1_000_003
+    r = np.zeros((3, n))
+    v = np.zeros((3, n))
+    v[0] = u.C_LIGHT
+    E = np.random.default_rng(5).uniform(0.5, 1.0, n) if wave else None
+    k = 1.0e-6 * (4.0 if wave else 1.0)  # ~30 % scatter per step (wave: e^4 ~ 0.06 .. 1)
+    runs = {}
+    for name, mode in (("tab", wave), ("sfu", wave | _capi.SCATTER_SFU)):
+        st, g = u.make_store(ctx, r, v, E=E, nscat=True)
+        sp = _capi.ScatterParams(k=k, c=u.C_LIGHT, mode=mode)
+        pl = _capi.make_planes([])
+        steps = 9
+        first = st.new_rows(steps)
+        soa = g.soa()
+        soa.dx = soa.dy = soa.dz = None
+        rg = _capi.Rng(seed=77, step=0)
+        ctx.call("pcl_photon_steps", st.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0),
+                 C.byref(pl), st.row_ptr(first), C.c_uint32(1))
+        one = {nm: g.download(nm).copy() for nm in u.PLANE_NAMES + ("nscat",)}
+        rg = _capi.Rng(seed=77, step=1)
+        ctx.call("pcl_photon_steps", st.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0),
+                 C.byref(pl), st.row_ptr(first + 1), C.c_uint32(8))
+        rows = np.array([st.read_row(first + i) for i in range(steps)])
+        runs[name] = (one, rows, {nm: g.download(nm).copy() for nm in u.PLANE_NAMES + ("nscat",)})
+    (one_t, rows_t, end_t), (one_s, rows_s, end_s) = runs["tab"], runs["sfu"]
+    # first timestep: identical decisions, positions and scatter counts; velocities of scattered photons agree closely
+    assert np.array_equal(rows_t[0][[_capi.T_ALIVE, _capi.T_SCATTERED, _capi.T_LIVE_IN]], rows_s[0][[_capi.T_ALIVE, _capi.T_SCATTERED, _capi.T_LIVE_IN]])
+    assert np.array_equal(one_t["nscat"], one_s["nscat"]) and 0.15 * n < one_t["nscat"].sum() < 0.6 * n
+    for nm in ("x", "y", "z"):
+        assert u.same_bits(one_t[nm], one_s[nm]), nm
+    hit = one_t["nscat"] == 1
+    vt = np.stack([one_t[q][hit] for q in ("vx", "vy", "vz")]).astype(np.float64)
+    vs = np.stack([one_s[q][hit] for q in ("vx", "vy", "vz")]).astype(np.float64)
+    assert np.abs(vs - vt).max() <= 2e-6 * u.C_LIGHT
+    assert np.abs(np.linalg.norm(vs, axis=0) / u.C_LIGHT - 1.0).max() <= 1e-5
+    assert not np.array_equal(vs, vt)  # the SFU form really ran
+    for q in ("vx", "vy", "vz"):  # untouched photons keep their bits
+        assert u.same_bits(one_s[q][~hit], one_t[q][~hit])
+    # nine timesteps: same law
+    sc_t, sc_s = rows_t[:, _capi.T_SCATTERED].sum(), rows_s[:, _capi.T_SCATTERED].sum()
+    assert abs(int(sc_t) - int(sc_s)) < 5 * np.sqrt(2.0 * sc_t)
+    moved = end_s["nscat"] > 0
+    vz = end_s["vz"][moved].astype(np.float64) / u.C_LIGHT
+    ks = stats.kstest(vz[:200_000], lambda x: 0.5 + np.arcsin(np.clip(x, -1, 1)) / np.pi)  # cos(theta), theta ~ U[0, 2 pi)
+    assert ks.pvalue > 1e-4, ks
+    # sign tallies of the last row: v_x balanced, v_y > 0 for every scattered photon with sin(theta) > 0 ...: compare forms
+    for col in (_capi.T_XP, _capi.T_YP, _capi.T_ZP):
+        a, b = int(rows_t[-1][col]), int(rows_s[-1][col])
+        assert abs(a - b) < 5 * np.sqrt(a + b + 1.0)
+
+
+def test_sfu_flag_is_rejected_where_it_cannot_apply(ctx):
+    """The stand-alone scatter kernel and injected uniforms keep the reproducible table: asking for the SFU there fails loudly."""
+    from physicl_b200 import _capi
+
+    u = _u()
+    n = 4096
+    r, v = u.random_photons(n, seed=3)
+    st, g = u.make_store(ctx, r, v)
+    g.ensure("dx", "dy", "dz")
+    sp = _capi.ScatterParams(k=1e-6, c=u.C_LIGHT, mode=_capi.SCATTER_SFU)
+    rg = _capi.Rng(seed=1, step=0)
+    soa = g.soa()
+    with pytest.raises(_capi.PclError, match="SFU"):
+        ctx.call("pcl_scatter", st.stream(), C.byref(soa), C.byref(sp), C.byref(rg), None, st.row_ptr(st.new_row()))
+    un = [torch.rand(n, device=st.device) for _ in range(3)]
+    rg.u_theta, rg.u_phi, rg.u_rand = (t.data_ptr() for t in un)
+    soa.dx = soa.dy = soa.dz = None
+    with pytest.raises(_capi.PclError, match="SFU"):
+        ctx.call("pcl_photon_step", st.stream(), C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(0.0),
+                 C.byref(_capi.make_planes([])), st.row_ptr(st.new_row()))
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("n", [3, 1024, 70_001])
 def test_timesteps_fused_in_registers_equal_single_steps(ctx, mode, n):

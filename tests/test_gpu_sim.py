@@ -839,3 +839,37 @@ def test_pulled_objects_carry_dv():
                 assert not np.any(dv)
         prev = [v for v, _ in step]
     assert 0.2 * 1600 < scattered < 0.4 * 1600
+
+
+def test_sfu_trig_option_through_the_simulation_api():
+    """ScatterIsotropicStep(sfu_trig=True): same pipeline, directions from the SFU.  The first row (no photon has a new
+    direction yet when it is decided) equals the default run's in its decision columns, the sign tallies stay balanced
+    the same way, and an unfused pipeline refuses the option loudly."""
+    n, steps, C_LIGHT = 200_000, 12, 299792458.0
+
+    def run(sfu, fuse=True):
+        sim = phys.Simulation(cl_on=True, seed=99, fuse=fuse, exit=lambda s: len(s.ts) >= steps)
+        r = np.zeros((3, n), np.float32)
+        v = np.zeros((3, n), np.float32)
+        v[0] = C_LIGHT
+        sim.add_particles(r, v)
+        sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+        sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+        sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3), sfu_trig=sfu))
+        sign = phys.light.ScatterSignMeasureStep(None, True)
+        sim.add_step(3, sign)
+        sim.start()
+        sim.join()
+        return np.array([[float(x) for x in row] for row in sign.data]), sim.device_store().snapshot("photon")
+
+    rows_t, snap_t = run(False)
+    rows_s, snap_s = run(True)
+    assert rows_t.shape == rows_s.shape == (steps, 5)
+    assert np.array_equal(rows_t[:, :2], rows_s[:, :2])  # t, N
+    assert not np.array_equal(snap_t["vx"], snap_s["vx"])  # the option reached the kernel
+    speed = np.sqrt(snap_s["vx"].astype(np.float64) ** 2 + snap_s["vy"].astype(np.float64) ** 2 + snap_s["vz"].astype(np.float64) ** 2)
+    assert np.abs(speed / C_LIGHT - 1.0).max() <= 1e-5
+    for col in (2, 3, 4):  # sign counts agree in law: differences within 5 sigma of two binomial counts
+        assert np.all(np.abs(rows_t[:, col] - rows_s[:, col]) < 5 * np.sqrt(rows_t[:, col] + rows_s[:, col] + 1.0))
+    with pytest.raises(Exception, match="SFU"):
+        run(True, fuse=False)
