@@ -107,6 +107,17 @@ class Object:
             setattr(self, attr, val)
 
 
+def _gather3(objs, attr):
+    """(3, N) float64 array of a 3-vector attribute of every object (code units: a Measurement's stored values)."""
+    try:  # the common case, all (3,) arrays: one C-level conversion of the list
+        out = np.array([getattr(o, attr) for o in objs], dtype=np.float64)
+        if out.shape == (len(objs), 3):
+            return out.T
+    except (TypeError, ValueError):
+        pass
+    return np.array([np.asarray(getattr(o, attr), np.float64) for o in objs]).reshape(-1, 3).T
+
+
 class _ObjectList(list):
     """``sim.objects``: a list that knows when the device store is the authority.
 
@@ -291,16 +302,19 @@ class Simulation(threading.Thread):
             if group:
                 lo, hi = self._shard_slice(len(group))
                 mine = group[lo:hi]
-                r = np.array([np.asarray(o.r, np.float64) for o in mine]).reshape(-1, 3).T
-                v = np.array([np.asarray(o.v, np.float64) for o in mine]).reshape(-1, 3).T
+                r = _gather3(mine, "r")
+                v = _gather3(mine, "v")
                 E = None
                 if kind == "photon":
-                    E = np.array([np.nan if getattr(o, "E", None) is None else float(np.asarray(o.E)) for o in mine])
-                a = np.array([np.asarray(o.a, np.float64) for o in mine]).reshape(-1, 3).T
+                    try:  # every photon has a numeric E: one C-level conversion
+                        E = np.array([o.E for o in mine], dtype=np.float64).reshape(len(mine))
+                    except (AttributeError, TypeError, ValueError):  # E = None is allowed (planck_phot_distribution may return it)
+                        E = np.array([np.nan if getattr(o, "E", None) is None else float(np.asarray(o.E)) for o in mine])
+                a = _gather3(mine, "a")
                 g = store.add_group(kind, r, v, E=E, a=a if np.any(a) else None, id_base=lo, host_objs=mine)
                 # Object.dr (physicl/__init__.py:391) is state too: measure steps that run after a host step read the
                 # displacement of this timestep (light.py:385-399), so it travels with the rebuild
-                dr = np.array([np.asarray(o.dr, np.float64) for o in mine]).reshape(-1, 3).T
+                dr = _gather3(mine, "dr")
                 if np.any(dr):
                     for q, nm in enumerate(("dx", "dy", "dz")):
                         g.upload(nm, dr[q])
