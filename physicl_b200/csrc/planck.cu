@@ -26,6 +26,8 @@
 // bit-exact against the oracle's linear scan of the reference's rule.
 // Traffic: 4 B written per photon (+4 B with bin_out).  Measured (64 Mi photons, 50 000 bins): 218 us = 308 G photons/s
 // (one Philox block per photon and float64 probes through L1/L2: 450 us); shared-memory wavefronts 63 %, issue 67 %.
+// Also measured: serving the crowded-bucket photons warp-wide (owner's range broadcast, one entry per lane, ballot
+// count) instead of per-lane searches: 251 us -- the shuffles and votes cost more than the divergent loops.
 #include "pcl_common.cuh"
 
 #define PCL_GUIDE_BITS 16
