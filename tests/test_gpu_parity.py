@@ -350,6 +350,32 @@ def test_compaction_is_stable_and_exact(ctx, n):
         assert u.same_bits(g.download(nm), again[nm]), nm
 
 
+@pytest.mark.parametrize("n", [5, 1024, 4097, 300_001])
+def test_compaction_carries_acceleration_and_displacement_planes(ctx, n):
+    """Groups with a and dr planes (kinematics with per-particle acceleration, unfused pipelines) take the kernel form with
+    all fifteen planes: every plane of every survivor arrives, in order, bit for bit."""
+    u = _u()
+    rng = np.random.default_rng(n + 1)
+    r, v = u.random_photons(n, seed=n + 1)
+    a = rng.normal(0, 3, (3, n))
+    st, g = u.make_store(ctx, r, v, E=np.linspace(0.5, 1.5, n), a=a, nscat=True)
+    g.ensure("dx", "dy", "dz")
+    for q, nm in enumerate(("dx", "dy", "dz")):
+        g.upload(nm, rng.normal(0, 1, n).astype(np.float32) + q)
+    dead = rng.random(n) < 0.6
+    x = g.download("x").copy()
+    x[dead] = np.nan
+    g.upload("x", x)
+    before = u.host_state(g)
+    assert {"ax", "ay", "az", "dx", "dy", "dz", "e", "nscat"} <= set(before)
+    n_live = st.compact("photon")
+    keep = ~dead
+    assert n_live == int(keep.sum()) == g.n
+    assert np.array_equal(g.download("id"), np.nonzero(keep)[0].astype(np.uint32))
+    for nm in before:
+        assert u.same_bits(g.download(nm), before[nm][keep]), nm
+
+
 def test_tallies_do_not_depend_on_compaction(ctx):
     u = _u()
     n = 120_000
