@@ -115,7 +115,9 @@ def _gather3(objs, attr):
             return out.T
     except (TypeError, ValueError):
         pass
-    return np.array([np.asarray(getattr(o, attr), np.float64) for o in objs]).reshape(-1, 3).T
+    if not objs:
+        return np.zeros((3, 0))
+    return np.array([np.asarray(getattr(o, attr), np.float64).reshape(3) for o in objs]).T  # lists, (3, 1) columns, ...
 
 
 class _ObjectList(list):

@@ -487,6 +487,13 @@ def test_planck_sampler_forms_bit_exact_vs_linear_scan(ctx, kind, ncdf, n, id_ba
     e_or, b_or = oracle.planck_sample(n, id_base, 99, cdf, np.float32(0.25), np.float32(1e-5))
     assert np.array_equal(b, b_or)
     assert np.array_equal(np.isnan(e), b < 0) and _u().same_bits(e[b >= 0], e_or[b >= 0])
+    # the same draw without the bin output (the form bulk emission uses): identical energies
+    e2 = torch.full((n + 2 * pad,), -7.0, dtype=torch.float32, device=dev)
+    ctx.call("pcl_planck_sample", stream, C.c_uint64(n), C.c_uint64(id_base), C.c_uint64(99), C.c_void_p(cdf_d.data_ptr()),
+             C.c_uint32(ncdf), C.c_float(0.25), C.c_float(1e-5), C.c_void_p(e2[pad:].data_ptr()), None)
+    torch.cuda.synchronize()
+    e2 = e2.cpu().numpy()
+    assert (e2[:pad] == -7).all() and (e2[pad + n:] == -7).all() and _u().same_bits(e2[pad:pad + n], e)
     if kind == "grid" :
         # the closed interval of the reference: some uniforms equal a table entry and must take the LOWER bin
         m = np.round(cdf * 2.0 ** 24).astype(np.int64)

@@ -285,6 +285,26 @@ def test_no_cpu_fallback_without_gpu():
         phys.Simulation(cl_on=True)
 
 
+def test_object_attribute_gather_fast_and_fallback_paths():
+    """_gather3 (the store is built from sim.objects with it): Measurements, plain arrays, lists and (3, 1) columns all
+    end up as one (3, N) float64 array, whichever conversion path is taken."""
+    from physicl_b200 import _gather3
+
+    class O:
+        pass
+
+    vals = [phys.Measurement([1, 2, 3], "m**1"), np.array([4.0, 5.0, 6.0]), [7, 8, 9], np.array([[10.0], [11.0], [12.0]])]
+    objs = []
+    for v in vals:
+        o = O()
+        o.r = v
+        objs.append(o)
+    want = np.array([[1, 4, 7, 10], [2, 5, 8, 11], [3, 6, 9, 12]], np.float64)
+    assert np.array_equal(_gather3(objs[:2], "r"), want[:, :2])  # fast path: every entry is a (3,) array
+    assert np.array_equal(_gather3(objs, "r"), want)             # ragged shapes: per-object conversion
+    assert _gather3([], "r").shape == (3, 0)
+
+
 def test_api_surface_covers_the_reference():
     """Every module-level name of the reference's physicl/__init__.py, light.py and newton.py exists here, every
     method of every class too, with the reference's positional parameters first and in the same order (so a call
