@@ -1,6 +1,7 @@
 """Randomised parity soak (GPU box): random sizes, modes, plane sets and timestep counts through the C ABI against the
 CPU oracle, bit for bit, for a given number of seconds.  Covers the fused photon steps (in place, several timesteps per
-launch), the stable compaction, the host-buffer kinematics and the emission sampler.  Prints one line per case family.
+launch; and through the compacting host-buffer entry point), the stable compaction, the host-buffer kinematics and the
+emission sampler.  Prints one summary line.
 usage: python scripts/fuzz_parity.py [seconds] [seed]"""
 import ctypes as C
 import os
@@ -21,7 +22,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 ctx = _capi.Context(0)
 dev = torch.device("cuda", 0)
-counts = {"photon_steps": 0, "compact": 0, "kinematics_host": 0, "planck": 0}
+counts = {"photon_host_compact": 0, "photon_steps": 0, "compact": 0, "kinematics_host": 0, "planck": 0}
 
 
 def pick_n():
@@ -142,7 +143,58 @@ def case_planck():
     assert u.same_bits(e[pad:pad + n], e_or)
 
 
-cases = [("photon_steps", case_photon_steps), ("compact", case_compact), ("kinematics_host", case_kinematics_host), ("planck", case_planck)]
+def case_photon_host_compact():
+    """pcl_photon_steps_host_compact (chunked H2D -> fused launch with retirement -> survivors D2H) against the twin."""
+    n, mode = pick_n(), int(rng.integers(0, 4))
+    r, v = u.random_photons(n, seed=int(rng.integers(1 << 30)), spread=float(rng.choice([1e3, 2e5])))
+    wave = bool(mode & 1)
+    E = rng.uniform(0.2, 1.0, n) if wave else None
+    k = float(rng.choice([2e-7, 2.5e-6]))
+    r2 = float(rng.choice([0.0, (1.5e6) ** 2, (3e5) ** 2]))
+    planes = [(int(rng.integers(0, 3)), float(rng.normal(0, 1e5))) for _ in range(int(rng.integers(0, 3)))]
+    id_base = int(rng.choice([0, 99, (3 << 32) + 11]))
+    chunk = int(rng.choice([4096, 32_768, 1 << 20]))
+    st, g = u.make_store(ctx, r, v, E=E, id_base=id_base)
+    twin = u.host_state(g)
+    twin["id"] = np.arange(n, dtype=np.uint32)
+    names = list(u.PLANE_NAMES) + (["e"] if wave else [])
+    host = {nm: torch.from_numpy(twin[nm].copy()) for nm in names}
+    host["id"] = torch.arange(n, dtype=torch.int32)
+    if rng.random() < 0.5:
+        host = {nm: t.pin_memory() for nm, t in host.items()}
+    sp = _capi.ScatterParams(k=k, c=u.C_LIGHT, mode=mode)
+    pl = _capi.make_planes(planes)
+    rows = np.zeros((8, _capi.TALLY_COLS), np.int64)
+    n_out = C.c_uint64(0)
+    seed, s, n_live = int(rng.integers(1 << 40)), int(rng.integers(1 << 20)), n
+    for _ in range(int(rng.integers(1, 4))):
+        m = int(rng.integers(1, 9))
+        soa = _capi.Soa()
+        soa.n, soa.id_base = n_live, id_base
+        for nm, t in host.items():
+            setattr(soa, nm, t.data_ptr())
+        rg = _capi.Rng(seed=seed, step=s)
+        ctx.call("pcl_photon_steps_host_compact", C.byref(soa), C.c_float(1e-3), C.byref(sp), C.byref(rg), C.c_float(r2), C.byref(pl),
+                 rows.ctypes.data_as(C.c_void_p), C.c_uint64(chunk), C.c_uint32(m), C.byref(n_out))
+        for q in range(m):
+            row_t = oracle.photon_step_f32(twin, 1e-3, k, u.C_LIGHT, mode, seed=seed, step=s + q, r2_escape=np.float32(r2), planes=planes,
+                                           id_base=id_base)
+            assert np.array_equal(rows[q], row_t), ("host row", n, mode, m, q, rows[q], row_t)
+        s += m
+        n_live = int(n_out.value)
+        live = ~np.isnan(twin["x"])
+        assert n_live == int(live.sum()), (n_live, int(live.sum()))
+        ids = host["id"].numpy()[:n_live].view(np.uint32)
+        order = np.argsort(ids)
+        assert np.array_equal(ids[order], np.nonzero(live)[0].astype(np.uint32))
+        for nm in names:
+            assert u.same_bits(host[nm].numpy()[:n_live][order], twin[nm][live]), (nm, n, mode, m)
+        # the twin carries on with the survivors only, in id order, like the host planes after sorting would
+        if n_live == 0:
+            break
+
+
+cases = [("photon_host_compact", case_photon_host_compact), ("photon_steps", case_photon_steps), ("compact", case_compact), ("kinematics_host", case_kinematics_host), ("planck", case_planck)]
 t0 = time.time()
 while time.time() - t0 < budget:
     name, fn = cases[int(rng.integers(0, len(cases)))]
