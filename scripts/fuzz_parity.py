@@ -18,11 +18,10 @@ import gpu_util as u
 import oracle
 from physicl_b200 import _capi
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
-ctx = _capi.Context(0)
-dev = torch.device("cuda", 0)
-counts = {"photon_host_compact": 0, "photon_steps": 0, "compact": 0, "kinematics_host": 0, "planck": 0}
+PLANCK_MAX_WORK = 2.4e10  # photons x table entries per emission case (the test suite lowers it)
+rng = np.random.default_rng(2026)  # re-seeded by main()
+ctx = None
+dev = None
 
 
 def pick_n():
@@ -120,7 +119,7 @@ def case_kinematics_host():
 def case_planck():
     ncdf = int(rng.choice([1, 2, 199, 999, 5000, 49_999, 65_535, 65_536, 70_000]))
     n = int(rng.choice([pick_n(), rng.integers(262_144, 400_000)]))
-    n = min(n, int(2.4e10 // max(ncdf, 1)))  # the oracle scans linearly: a few seconds at most
+    n = min(n, int(PLANCK_MAX_WORK // max(ncdf, 1)))  # the oracle scans linearly: a few seconds at most
     w = rng.uniform(0.0, 1.0, ncdf) ** float(rng.choice([1.0, 8.0, 40.0]))
     w[rng.integers(0, ncdf)] += 1e-3
     cdf = np.cumsum(w / w.sum())
@@ -194,10 +193,28 @@ def case_photon_host_compact():
             break
 
 
-cases = [("photon_host_compact", case_photon_host_compact), ("photon_steps", case_photon_steps), ("compact", case_compact), ("kinematics_host", case_kinematics_host), ("planck", case_planck)]
-t0 = time.time()
-while time.time() - t0 < budget:
-    name, fn = cases[int(rng.integers(0, len(cases)))]
-    fn()
-    counts[name] += 1
-print("fuzz ok in %.0f s: %s" % (time.time() - t0, counts))
+CASES = [("photon_host_compact", case_photon_host_compact), ("photon_steps", case_photon_steps), ("compact", case_compact),
+         ("kinematics_host", case_kinematics_host), ("planck", case_planck)]
+
+
+def main(budget=60.0, seed=2026, device=0):
+    """Run random cases for `budget` seconds; returns the number of cases per family (raises on the first mismatch)."""
+    global rng, ctx, dev
+    rng = np.random.default_rng(seed)
+    ctx = _capi.Context(device)
+    dev = torch.device("cuda", device)
+    counts = {name: 0 for name, _ in CASES}
+    t0 = time.time()
+    try:
+        while time.time() - t0 < budget:
+            name, fn = CASES[int(rng.integers(0, len(CASES)))]
+            fn()
+            counts[name] += 1
+    finally:
+        ctx.close()
+    return counts, time.time() - t0
+
+
+if __name__ == "__main__":
+    counts, secs = main(float(sys.argv[1]) if len(sys.argv) > 1 else 60.0, int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
+    print("fuzz ok in %.0f s: %s" % (secs, counts))
