@@ -34,7 +34,10 @@ class IndexException(NameError):
 class Step:
     """Plugin protocol of the reference (physicl/__init__.py:293-322): ``run(sim)`` once per
     timestep, ``terminate(sim)`` once at the end.  ``uses_device`` marks steps that operate on the
-    HBM-resident store; everything else is treated as a host step that reads ``sim.objects``."""
+    HBM-resident store; everything else is treated as a host step that reads ``sim.objects``: the objects are made
+    current before it runs and re-uploaded before the next device step.  A host step that only READS the objects (a
+    measurement written in Python) can set ``modifies_objects = False`` to skip that re-upload (new, optional; the
+    default is the safe one)."""
 
     uses_device = False
 
@@ -488,7 +491,10 @@ class Simulation(threading.Thread):
                         for step in plan:
                             if not step.uses_device and getattr(step, "touches_objects", True):
                                 self._pull_objects()
-                                self._host_dirty = self._host_dirty or self.store is not None
+                                # a host step may change the objects: the store is rebuilt from them before the next device
+                                # step -- unless the step says it only reads (modifies_objects = False, see Step)
+                                if getattr(step, "modifies_objects", True):
+                                    self._host_dirty = self._host_dirty or self.store is not None
                             step.run(self)
                         self.step_index += 1
             with self._state_lock:
@@ -625,7 +631,8 @@ class Simulation(threading.Thread):
             for step in plan:
                 if not step.uses_device and getattr(step, "touches_objects", True):
                     self._pull_objects()
-                    self._host_dirty = self._host_dirty or self.store is not None
+                    if getattr(step, "modifies_objects", True):
+                        self._host_dirty = self._host_dirty or self.store is not None
                 step.run(self)
             self.step_index += 1
 

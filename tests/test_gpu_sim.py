@@ -873,3 +873,45 @@ def test_sfu_trig_option_through_the_simulation_api():
         assert np.all(np.abs(rows_t[:, col] - rows_s[:, col]) < 5 * np.sqrt(rows_t[:, col] + rows_s[:, col] + 1.0))
     with pytest.raises(Exception, match="SFU"):
         run(True, fuse=False)
+
+
+def test_read_only_host_step_skips_the_reupload():
+    """A Python measurement step that only reads sim.objects (modifies_objects = False): the objects are current when it
+    runs, the device store is NOT rebuilt from them afterwards, and the physics is the run without that step, row for row.
+    The same step without the declaration forces a rebuild every timestep (the safe default) and gives the same rows."""
+    n, steps = 3000, 6
+
+    class MeanX(phys.MeasureStep):
+        def __init__(self, read_only):
+            super().__init__(None)
+            if read_only:
+                self.modifies_objects = False
+            self.stores = []
+
+        def run(self, sim):
+            self.data.append(float(np.mean([float(o.r[0]) for o in sim.objects])))
+            self.stores.append(sim.store)  # kept alive, so that identities cannot be recycled
+
+    def run(host_step):
+        sim = phys.Simulation(cl_on=True, seed=5, exit=lambda s: len(s.ts) >= steps)
+        for _ in range(n):
+            sim.add_obj(phys.light.PhotonObject(v=np.array([phys.light.c, 0, 0], dtype=np.double), E=np.double(1)))
+        sim.add_step(0, phys.UpdateTimeStep(lambda s: np.double(1e-3)))
+        sim.add_step(1, phys.newton.NewtonianKinematicsStep())
+        sim.add_step(2, phys.light.ScatterIsotropicStep(A=np.double(1e-3), n=np.double(1e-3)))
+        sign = phys.light.ScatterSignMeasureStep(None, True)
+        sim.add_step(3, sign)
+        if host_step is not None:
+            sim.add_step(4, host_step)
+        sim.start()
+        sim.join()
+        return np.array([[float(x) for x in row] for row in sign.data])
+
+    base = run(None)
+    ro, rw = MeanX(True), MeanX(False)
+    rows_ro, rows_rw = run(ro), run(rw)
+    assert np.array_equal(rows_ro, base) and np.array_equal(rows_rw, base)
+    assert len(ro.data) == steps and np.allclose(ro.data, rw.data, rtol=0, atol=0)
+    assert ro.data[0] > 0 and ro.data[-1] != ro.data[0]          # the objects were current every time it looked
+    assert len({id(x) for x in ro.stores}) == 1                    # one store for the whole run
+    assert len({id(x) for x in rw.stores}) == steps                # rebuilt after every host step
